@@ -1,0 +1,191 @@
+/*
+ * dcs_b200.h — C-ABI of the B200-native DCS-LM hot path (libdcs_b200.so).
+ *
+ * This is the drop-in boundary for the part of the reference that runs inside
+ * ceres::Solve.  The reference has no FFI of its own: its boundary is the Ceres
+ * call surface that DCS-ceres/main.cpp touches.  Each entry point below names the
+ * reference call(s) it replaces (paths relative to the reference checkout):
+ *
+ *   dcs_create      <- ceres::Problem ctor (main.cpp:66), new HuberLoss(0.01) (:68),
+ *                      OdometryResidue::Create / DCSClosureResidue::Create
+ *                      (:98,:113,:127,:136,:147; src/ceres_error.cpp:28-39,121-132),
+ *                      Problem::AddResidualBlock (:99,:114,:128,:137,:148),
+ *                      SetParameterBlockConstant (:153), Solver::Options (:154-156)
+ *   dcs_evaluate    <- Problem::Evaluate / ResidualBlock::Evaluate of the two functors
+ *                      (src/ceres_error.cpp:42-94, :135-196) + HuberLoss Corrector
+ *   dcs_solve       <- ceres::Solve(options,&problem,&summary) (main.cpp:163)
+ *   dcs_get_pattern <- the block structure Ceres' SPARSE_NORMAL_CHOLESKY builds for J^T J
+ *                      (main.cpp:156)
+ *   dcs_destroy     <- ~Problem
+ *
+ * Plain pointers and sizes only; every function returns an int status (0 = ok); no
+ * exceptions cross the boundary.  All array arguments are HOST pointers unless the
+ * name ends in _dev.  There is no CPU fallback: every compute entry point fails with
+ * DCS_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef DCS_B200_H
+#define DCS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  DCS_OK = 0,
+  DCS_ERR_ARG = 1,      /* null pointer, bad index, a == b edge, ...            */
+  DCS_ERR_CUDA = 2,     /* CUDA runtime error / no device (no CPU fallback)     */
+  DCS_ERR_NCCL = 3,     /* NCCL missing or failed (multi-rank handles only)     */
+  DCS_ERR_NUMERIC = 4   /* non-finite cost at the initial point                 */
+};
+
+/* Edge kinds — reference include/g2o_util.h:13-15 */
+enum { DCS_EDGE_ODOMETRY = 0, DCS_EDGE_CLOSURE = 1, DCS_EDGE_BOGUS = 2 };
+
+/* Termination — mirrors ceres::TerminationType as used by the default minimizer */
+enum {
+  DCS_CONVERGENCE = 0,
+  DCS_NO_CONVERGENCE = 1,
+  DCS_FAILURE = 2
+};
+
+/* Flattened view of the reference's Node / Edge pointer graph (include/graph.h:4-56).
+ * Information matrices are not part of it: METHOD 0/1 never read them. */
+typedef struct dcs_graph {
+  int32_t n_poses;
+  int32_t n_edges;
+  const double* pose_xyt;   /* n_poses x 3, row-major (x, y, theta); copied in          */
+  const int32_t* edge_a;    /* first endpoint  (Edge::a->index)                          */
+  const int32_t* edge_b;    /* second endpoint (Edge::b->index)                          */
+  const double* meas_xyt;   /* n_edges x 3 (Edge::x, y, theta)                           */
+  const uint8_t* kind;      /* DCS_EDGE_*; order = odometry, closure, bogus (main.cpp)   */
+  int32_t fixed_pose;       /* parameter block held constant (main.cpp:153 -> 0)         */
+} dcs_graph;
+
+typedef struct dcs_options {
+  /* residual model */
+  int32_t dcs_on;                 /* METHOD==1 (main.cpp:55)                             */
+  double phi;                     /* 0.5  (src/ceres_error.cpp:185)                      */
+  double huber_delta;             /* 0.01 (main.cpp:68)                                  */
+  /* trust-region LM — Ceres defaults implied by main.cpp:154-156                         */
+  int32_t max_num_iterations;     /* 50                                                  */
+  double initial_trust_region_radius; /* 1e4                                             */
+  double max_trust_region_radius;     /* 1e16                                            */
+  double min_trust_region_radius;     /* 1e-32                                           */
+  double min_relative_decrease;       /* 1e-3                                            */
+  double min_lm_diagonal;             /* 1e-6                                            */
+  double max_lm_diagonal;             /* 1e32                                            */
+  double function_tolerance;          /* 1e-6                                            */
+  double gradient_tolerance;          /* 1e-10                                           */
+  double parameter_tolerance;         /* 1e-8                                            */
+  int32_t max_num_consecutive_invalid_steps; /* 5                                        */
+  int32_t jacobi_scaling;             /* 1                                               */
+  /* linear solver: block-Jacobi PCG on the 3x3-block normal equations                    */
+  double pcg_rel_tol;             /* stop when |r|_2 <= pcg_rel_tol * |rhs|_2            */
+  int32_t pcg_max_iter;
+  int32_t pcg_check_every;        /* iterations per graph launch between host checks     */
+  /* execution */
+  int32_t device;                 /* CUDA device ordinal                                 */
+  int32_t verbose;                /* 1: Ceres-style progress table on stdout             */
+  /* multi-GPU: one process per GPU. world==1 -> single device.                           */
+  int32_t rank;
+  int32_t world;
+  const void* nccl_unique_id;     /* 128-byte ncclUniqueId shared by all ranks           */
+} dcs_options;
+
+typedef struct dcs_iteration {
+  int32_t iteration;
+  int32_t step_is_valid;
+  int32_t step_is_successful;
+  int32_t linear_solver_iterations;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+  double linear_solver_residual;  /* final PCG |r|/|rhs|                                 */
+  double iteration_time_s;
+  double cumulative_time_s;
+} dcs_iteration;
+
+typedef struct dcs_summary {
+  double initial_cost;
+  double final_cost;
+  int32_t num_iterations;         /* entries written to the trace (iteration 0 included) */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t termination_type;       /* DCS_CONVERGENCE / DCS_NO_CONVERGENCE / DCS_FAILURE  */
+  int64_t total_pcg_iterations;
+  double total_time_s;
+  double eval_time_s;             /* device time in eval+assembly launches               */
+  double linear_solver_time_s;    /* device time in PCG                                  */
+  char message[128];
+} dcs_summary;
+
+typedef struct dcs_handle dcs_handle;
+
+/* Fill o with the reference's defaults (see field comments). */
+void dcs_options_default(dcs_options* o);
+
+/* Library / device probes (no compute). */
+const char* dcs_version(void);
+int dcs_device_count(void);
+
+/* 128-byte id for a multi-rank group; rank 0 calls it and ships the bytes to the peers. */
+int dcs_nccl_unique_id(void* out128);
+
+/* Upload the graph, build the half-edge CSR and the block pattern (one-time sort). */
+int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out);
+void dcs_destroy(dcs_handle* h);
+
+/* Parity hook: evaluate at pose_xyt (NULL -> the handle's current poses).
+ * Any output pointer may be NULL.  Shapes: residuals E x 3, jacobians E x 18
+ * (row-major 3x6 per edge: d e / d(pa, pb), after DCS and the Huber corrector),
+ * psi E, rho1 E (Huber rho'), gradient N x 3 (zeros at the fixed pose). */
+int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost,
+                 double* residuals, double* jacobians, double* psi, double* rho1,
+                 double* gradient);
+
+/* Hot path on host buffers: H2D poses, fused eval + J^T J / J^T r assembly on device,
+ * D2H cost and gradient (either may be NULL).  The assembled H stays on the device. */
+int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* gradient);
+
+/* Same launches with everything resident on the device (used by bench.py's `value`). */
+int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total);
+
+/* Cost-only evaluation (candidate point inside LM). */
+int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost);
+
+/* Integer parity hook: upper block pattern of J^T J over the non-constant poses,
+ * {(i,i)} U {(min(a,b),max(a,b))}, as CSR over poses.  Call with NULL arrays to get
+ * the sizes; then with row_ptr[n_poses+1] and col_idx[nnzb]. */
+int dcs_get_pattern(dcs_handle* h, int32_t* n_block_rows, int32_t* nnzb,
+                    int32_t* row_ptr, int32_t* col_idx);
+
+/* Values of the assembled J^T J on that pattern (nnzb x 9, row-major 3x3), from the last
+ * dcs_linearize / dcs_evaluate / accepted LM step. */
+int dcs_get_hessian(dcs_handle* h, double* block_values);
+
+/* One linear solve (H + diag(lambda)) w = rhs with block-Jacobi PCG on the current H.
+ * lambda, rhs, w: N x 3 host arrays (entries of the fixed pose ignored / zero). */
+int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double* w,
+                  int32_t* iterations, double* rel_residual);
+
+/* Full DCS-LM solve. pose_xyt_inout: N x 3, updated in place (Node::p write-back,
+ * include/graph.h:10-17).  trace may be NULL; trace_cap entries are written at most. */
+int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* summary,
+              dcs_iteration* trace, int32_t trace_cap);
+
+/* Last CUDA / NCCL error text for this thread ("" if none). */
+const char* dcs_last_error(void);
+
+/* Number of kernel launches issued by this library since the counter was last reset. */
+int64_t dcs_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCS_B200_H */

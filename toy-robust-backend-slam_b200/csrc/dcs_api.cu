@@ -1,0 +1,963 @@
+// dcs_api.cu — C-ABI of libdcs_b200 (include/dcs_b200.h): graph upload + one-time pattern build,
+// the evaluate / linearize entry points, the block-Jacobi PCG driver (CUDA-graph batches, device
+// scalars) and the host-side Levenberg–Marquardt controller that follows Ceres' default
+// trust-region rules (reference call site DCS-ceres/main.cpp:154-163).
+//
+// No CPU fallback anywhere: every entry point that computes fails with DCS_ERR_CUDA if the CUDA
+// runtime does.  Nothing here includes, links or loads anything under oracle/.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/dcs_b200.h"
+#include "dcs_common.cuh"
+#include "dcs_kernels.cuh"
+#include "dcs_nccl.h"
+#include "dcs_pattern.cuh"
+
+using namespace dcs;
+
+namespace {
+
+thread_local std::string g_err;
+int64_t g_launches = 0;
+
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      return DCS_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+#define CKN(call)                                                                                \
+  do {                                                                                           \
+    ncclResult_t _r = (call);                                                                    \
+    if (_r != ncclSuccess) {                                                                     \
+      g_err = std::string(#call) + ": " + nccl_api().GetErrorString(_r);                         \
+      return DCS_ERR_NCCL;                                                                       \
+    }                                                                                            \
+  } while (0)
+#define CKS(call)                                                                                \
+  do {                                                                                           \
+    int _s = (call);                                                                             \
+    if (_s != DCS_OK) return _s;                                                                 \
+  } while (0)
+#define LAUNCH(kernel, grid, block, stream, ...)                                                 \
+  do {                                                                                           \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                       \
+    ++g_launches;                                                                                \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  cudaError_t alloc_zero(size_t count) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess || count == 0) return e;
+    return cudaMemset(p, 0, count * sizeof(T));
+  }
+};
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// per-edge constants: (tmx,tmy) = Rm^T (dx,dy), cos/sin of the measured rotation, DCS flag
+__global__ void k_edge_prep(const double* __restrict__ meas, const uint8_t* __restrict__ kind, int32_t E, int dcs_on,
+                            double* tmx, double* tmy, double* thm, double* cm, double* sm, uint8_t* dcs_flag) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const double dx = meas[3 * (int64_t)e], dy = meas[3 * (int64_t)e + 1], th = meas[3 * (int64_t)e + 2];
+  double s, c;
+  sincos(th, &s, &c);
+  tmx[e] = fma(c, dx, s * dy);
+  tmy[e] = fma(c, dy, -s * dx);
+  thm[e] = th; cm[e] = c; sm[e] = s;
+  dcs_flag[e] = (dcs_on && kind[e] != DCS_EDGE_ODOMETRY) ? 1 : 0;
+}
+
+// sorted half-edge i -> JDS slot: other word + measurement constants
+__global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const int32_t* __restrict__ slot,
+                                 int32_t nh, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
+                                 const int32_t* __restrict__ deg_all, int32_t fixed, const double* __restrict__ tmx,
+                                 const double* __restrict__ tmy, const double* __restrict__ thm, const double* __restrict__ cm,
+                                 const double* __restrict__ sm, const uint8_t* __restrict__ dcs_flag, uint32_t* h_other,
+                                 double* h_tmx, double* h_tmy, double* h_thm, double* h_cm, double* h_sm) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const uint32_t v = vals[i];
+  const int32_t e = (int32_t)(v >> 1);
+  const bool side_b = (v & 1u) != 0;
+  const int32_t other = (int32_t)(keys[i] & 0xFFFFFFFFu);
+  const int32_t a = ea[e];
+  uint32_t word = (uint32_t)other;
+  if (side_b) word |= kFlagSideB;
+  if (dcs_flag[e]) word |= kFlagDcs;
+  if (other == fixed) word |= kFlagOtherFixed;
+  // the edge's cost is booked on its a-side half-edge, or on the b side when a is constant
+  const bool a_has_row = (a != fixed);
+  if ((!side_b && a_has_row) || (side_b && !a_has_row)) word |= kFlagCost;
+  const int32_t s = slot[i];
+  h_other[s] = word;
+  h_tmx[s] = tmx[e]; h_tmy[s] = tmy[e]; h_thm[s] = thm[e]; h_cm[s] = cm[e]; h_sm[s] = sm[e];
+  (void)deg_all; (void)eb;
+}
+
+__global__ void k_is_free(const int32_t* __restrict__ deg_all, int32_t row_lo, int32_t nrows, int32_t fixed, uint8_t* is_free) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  is_free[r] = (deg_all[row_lo + r] > 0 && (row_lo + r) != fixed) ? 1 : 0;
+}
+
+// parity hook: canonical upper pattern values. One thread per flagged (first-of-run) sorted half-edge.
+__global__ void k_export_upper(const uint64_t* __restrict__ keys, const int32_t* __restrict__ flag_scan, const int32_t* __restrict__ flag,
+                               const int32_t* __restrict__ slot, int32_t nh, const double* __restrict__ Hoff, int64_t ldh,
+                               double* out /* n_upper x 9 */) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh || !flag[i]) return;
+  const uint64_t k = keys[i];
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int32_t j = i; j < nh && keys[j] == k; ++j) {   // duplicate edges between the same pair add up
+    const int64_t s = slot[j];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] += Hoff[(int64_t)c * ldh + s];
+  }
+  double* o = out + 9 * (int64_t)flag_scan[i];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) o[c] = acc[c];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+struct dcs_handle {
+  dcs_options opt;
+  Params P;
+  int32_t N = 0, E = 0, fixed = 0;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // partition (world == 1: everything)
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  int32_t rows_per_rank = 0, row_lo = 0, nrows = 0, Npad = 0;
+  int32_t e_lo = 0, e_hi = 0;
+  int32_t nblk = 0, nh = 0;
+  int64_t ldn = 0, ldh = 0;
+  // graph (device)
+  DevBuf<int32_t> ea, eb, deg_all;
+  DevBuf<double> e_tmx, e_tmy, e_thm, e_cm, e_sm;
+  DevBuf<uint8_t> e_dcs, is_free;
+  // pattern
+  DevBuf<uint64_t> keys;        // sorted (row<<32|col)
+  DevBuf<uint32_t> vals;        // edge<<1|side
+  DevBuf<int32_t> row_ptr, rp_off, round_ptr, slot, up_flag, up_scan;
+  DevBuf<uint8_t> rank_of, perm;
+  int32_t n_upper = 0;
+  // half-edges (JDS order)
+  DevBuf<uint32_t> h_other;
+  DevBuf<double> h_tmx, h_tmy, h_thm, h_cm, h_sm;
+  // state
+  DevBuf<double4> xyt, cand_xyt, p4;
+  DevBuf<double2> cs, cand_cs;
+  DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
+  DevBuf<double> partials, scal, stage3;   // stage3: N x 3 staging for host<->device AoS
+  DevBuf<unsigned int> tickets;
+  double* h_scal = nullptr;                // pinned mirror of scal
+  double* h_pin3 = nullptr;                // pinned N x 3 staging
+  cudaGraphExec_t pcg_graph = nullptr;
+  int pcg_graph_iters = 0;
+  const double* pcg_graph_D = nullptr;
+  bool have_lin = false;
+  double eval_ms = 0, pcg_ms = 0;
+  int64_t pcg_iters_total = 0;
+
+  RowLayout layout() const {
+    RowLayout L;
+    L.row_lo = row_lo; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;
+    L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
+    return L;
+  }
+  HalfEdges halfedges() const {
+    HalfEdges H;
+    H.other = h_other.p; H.tmx = h_tmx.p; H.tmy = h_tmy.p; H.thm = h_thm.p; H.cm = h_cm.p; H.sm = h_sm.p;
+    return H;
+  }
+  EdgeList edgelist() const {
+    EdgeList L;
+    L.n = E; L.a = ea.p; L.b = eb.p; L.tmx = e_tmx.p; L.tmy = e_tmy.p; L.thm = e_thm.p; L.cm = e_cm.p; L.sm = e_sm.p; L.dcs = e_dcs.p;
+    return L;
+  }
+  int vec_grid() const { return std::max(1, cdiv(nrows, kVecThreads)); }
+};
+
+namespace {
+
+int scan_exclusive(int32_t* d, int64_t n, cudaStream_t st) {
+  if (n <= 0) return DCS_OK;
+  const int nb = cdiv(n, kScanTile);
+  DevBuf<int32_t> totals;
+  CK(totals.alloc((size_t)nb));
+  LAUNCH(k_scan_tile, nb, kScanThreads, st, d, n, totals.p);
+  if (nb > 1) {
+    CKS(scan_exclusive(totals.p, nb, st));
+    LAUNCH(k_scan_add, nb, kScanThreads, st, d, n, totals.p);
+  }
+  CK(cudaStreamSynchronize(st));   // totals freed on return
+  return DCS_OK;
+}
+
+// stable LSD radix sort of (key,val) on the bit range [0,bits_lo) and [32,32+bits_hi)
+int radix_sort(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, int64_t n, int bits_lo, int bits_hi, cudaStream_t st) {
+  if (n <= 1) return DCS_OK;
+  DevBuf<uint64_t> k2;
+  DevBuf<uint32_t> v2;
+  CK(k2.alloc((size_t)n));
+  CK(v2.alloc((size_t)n));
+  const int nblk = cdiv(n, kSortTile);
+  DevBuf<int32_t> hist;
+  CK(hist.alloc((size_t)256 * nblk));
+  uint64_t* ki = keys.p; uint64_t* ko = k2.p;
+  uint32_t* vi = vals.p; uint32_t* vo = v2.p;
+  std::vector<int> shifts;
+  for (int s = 0; s < bits_lo; s += 8) shifts.push_back(s);
+  for (int s = 0; s < bits_hi; s += 8) shifts.push_back(32 + s);
+  for (int shift : shifts) {
+    LAUNCH(k_radix_hist, nblk, kSortThreads, st, ki, n, shift, hist.p, nblk);
+    CKS(scan_exclusive(hist.p, (int64_t)256 * nblk, st));
+    LAUNCH(k_radix_scatter, nblk, kSortThreads, st, ki, vi, ko, vo, n, shift, hist.p, nblk);
+    std::swap(ki, ko);
+    std::swap(vi, vo);
+  }
+  CK(cudaStreamSynchronize(st));
+  if (ki != keys.p) {   // odd number of passes: result lives in the scratch pair
+    std::swap(keys.p, k2.p);
+    std::swap(vals.p, v2.p);
+  }
+  CK(cudaGetLastError());
+  return DCS_OK;
+}
+
+int bits_for(int32_t n) { int b = 1; while ((1ll << b) < (long long)n) ++b; return b; }
+
+int allreduce_sum(dcs_handle* h, double* d, int count) {
+  if (h->world == 1) return DCS_OK;
+  CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
+  return DCS_OK;
+}
+int allreduce_max(dcs_handle* h, double* d, int count) {
+  if (h->world == 1) return DCS_OK;
+  CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclMax, h->comm, h->stream));
+  return DCS_OK;
+}
+// every rank owns rows [rank*rows_per_rank, ...) of a full-length array with `bytes_per_row`
+int allgather_rows(dcs_handle* h, void* full, size_t bytes_per_row) {
+  if (h->world == 1) return DCS_OK;
+  char* base = static_cast<char*>(full);
+  const size_t chunk = (size_t)h->rows_per_rank * bytes_per_row;
+  CKN(nccl_api().AllGather(base + (size_t)h->rank * chunk, base, chunk, ncclChar, h->comm, h->stream));
+  return DCS_OK;
+}
+
+int read_scalars(dcs_handle* h) {
+  CK(cudaMemcpyAsync(h->h_scal, h->scal.p, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DCS_OK;
+}
+
+// host N x 3 poses -> device packed poses (+ cos/sin)
+int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt, double2* cs) {
+  std::memcpy(h->h_pin3, pose_xyt, (size_t)h->N * 3 * sizeof(double));
+  CK(cudaMemcpyAsync(h->stage3.p, h->h_pin3, (size_t)h->N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(k_pack_poses, cdiv(h->N, 256), 256, h->stream, h->stage3.p, h->N, xyt, cs);
+  return DCS_OK;
+}
+int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
+  LAUNCH(k_unpack_poses, cdiv(h->N, 256), 256, h->stream, xyt, h->N, h->stage3.p);
+  CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::memcpy(pose_xyt, h->h_pin3, (size_t)h->N * 3 * sizeof(double));
+  return DCS_OK;
+}
+
+// K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
+int linearize(dcs_handle* h, const double4* xyt, const double2* cs) {
+  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, cs, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
+         h->grad.p, h->partials.p, h->tickets.p, h->scal.p);
+  CKS(allreduce_sum(h, h->scal.p + S_COST, 2));
+  CKS(allreduce_max(h, h->scal.p + S_GMAX, 1));
+  h->have_lin = true;
+  return DCS_OK;
+}
+
+int cost_only(dcs_handle* h, const double4* xyt, const double2* cs, int slot) {
+  const int ne = h->e_hi - h->e_lo;
+  const int grid = std::max(1, std::min(cdiv(ne, kEdgeThreads), 148 * 8));
+  LAUNCH(k_cost, grid, kEdgeThreads, h->stream, xyt, cs, h->edgelist(), h->e_lo, h->e_hi, h->P, h->partials.p, h->tickets.p + 2,
+         h->scal.p + slot);
+  CKS(allreduce_sum(h, h->scal.p + slot, 1));
+  return DCS_OK;
+}
+
+// one PCG iteration on the stream (capturable)
+int pcg_iteration(dcs_handle* h, const double* D) {
+  LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->partials.p,
+         h->tickets.p + 3, h->scal.p, (int)S_PQ, 1);
+  CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
+  LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, h->row_lo, h->nrows, h->ldn, h->w.p,
+         h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
+  CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
+  LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->scal.p);
+  CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
+  return DCS_OK;
+}
+
+// Solve (H + Lambda) w = rhs.  Lambda from (lmdiag, scale, radius) or explicit.  rhs: device SoA.
+int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, const double* rhs, int* iters_out,
+              double* relres_out) {
+  CK(cudaEventRecord(h->ev0, h->stream));
+  LAUNCH(k_precond, h->vec_grid(), 256, h->stream, h->Hdiag.p, h->lmdiag.p, h->scale.p, h->is_free.p, h->nrows, h->ldn, inv_radius,
+         lambda_explicit, h->Adiag.p, h->Minv.p);
+  LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->w.p, h->r.p,
+         h->z.p, h->p4.p, h->partials.p, h->tickets.p + 4, h->scal.p);
+  CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
+  LAUNCH(k_pcg_init_finish, 1, 1, h->stream, h->scal.p);
+  CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
+  CKS(read_scalars(h));
+  const double rr0 = h->h_scal[S_RR0];
+  int iters = 0;
+  double rr = rr0;
+  if (rr0 > 0.0 && std::isfinite(rr0)) {
+    const int batch = std::max(1, h->opt.pcg_check_every);
+    if (!h->pcg_graph || h->pcg_graph_iters != batch || h->pcg_graph_D != h->Adiag.p) {
+      if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      int st = DCS_OK;
+      for (int i = 0; i < batch && st == DCS_OK; ++i) st = pcg_iteration(h, h->Adiag.p);
+      cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+      if (st != DCS_OK) { if (g) cudaGraphDestroy(g); return st; }
+      CK(ce);
+      CK(cudaGraphInstantiate(&h->pcg_graph, g, 0));
+      CK(cudaGraphDestroy(g));
+      h->pcg_graph_iters = batch;
+      h->pcg_graph_D = h->Adiag.p;
+      g_launches -= 3LL * batch;   // capture does not launch
+    }
+    const double target = h->opt.pcg_rel_tol * h->opt.pcg_rel_tol * rr0;
+    while (iters < h->opt.pcg_max_iter) {
+      CK(cudaGraphLaunch(h->pcg_graph, h->stream));
+      g_launches += 3LL * batch;
+      iters += batch;
+      CKS(read_scalars(h));
+      rr = h->h_scal[S_RR];
+      if (!(rr > target)) break;   // converged, or NaN (caller validates the step)
+    }
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->pcg_ms += ms;
+  h->pcg_iters_total += iters;
+  if (iters_out) *iters_out = iters;
+  if (relres_out) *relres_out = (rr0 > 0.0) ? std::sqrt(rr / rr0) : 0.0;
+  return DCS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+void dcs_options_default(dcs_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->dcs_on = 1;
+  o->phi = 0.5;
+  o->huber_delta = 0.01;
+  o->max_num_iterations = 50;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->pcg_rel_tol = 1e-12;
+  o->pcg_max_iter = 200000;
+  o->pcg_check_every = 32;
+  o->device = 0;
+  o->verbose = 0;
+  o->rank = 0;
+  o->world = 1;
+  o->nccl_unique_id = nullptr;
+}
+
+const char* dcs_version(void) { return "dcs_b200 0.1 (sm_100a)"; }
+const char* dcs_last_error(void) { return g_err.c_str(); }
+int64_t dcs_launch_count(int reset) { const int64_t v = g_launches; if (reset) g_launches = 0; return v; }
+
+int dcs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int dcs_nccl_unique_id(void* out128) {
+  if (!out128) return DCS_ERR_ARG;
+  if (!nccl_api().load()) { g_err = "libnccl.so.2 not found"; return DCS_ERR_NCCL; }
+  ncclUniqueId id;
+  CKN(nccl_api().GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+  return DCS_OK;
+}
+
+void dcs_destroy(dcs_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->dev);
+  if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
+  if (h->comm) nccl_api().CommDestroy(h->comm);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_pin3) cudaFreeHost(h->h_pin3);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
+  if (!g || !o || !out || g->n_poses <= 0 || g->n_edges < 0 || !g->pose_xyt) { g_err = "dcs_create: bad argument"; return DCS_ERR_ARG; }
+  if (g->n_edges > 0 && (!g->edge_a || !g->edge_b || !g->meas_xyt || !g->kind)) { g_err = "dcs_create: null edge array"; return DCS_ERR_ARG; }
+  if ((uint32_t)g->n_poses > kIdxMask) { g_err = "dcs_create: too many poses"; return DCS_ERR_ARG; }
+  for (int32_t k = 0; k < g->n_edges; ++k) {
+    const int32_t a = g->edge_a[k], b = g->edge_b[k];
+    if (a < 0 || b < 0 || a >= g->n_poses || b >= g->n_poses || a == b) {
+      g_err = "dcs_create: edge " + std::to_string(k) + " has an invalid endpoint pair";   // Ceres aborts on a == b
+      return DCS_ERR_ARG;
+    }
+  }
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (o->device < 0 || o->device >= ndev) { g_err = "dcs_create: no such CUDA device"; return DCS_ERR_CUDA; }
+  CK(cudaSetDevice(o->device));
+
+  dcs_handle* h = new dcs_handle();
+  struct Guard { dcs_handle* h; ~Guard() { if (h) dcs_destroy(h); } } guard{h};
+  h->opt = *o;
+  h->opt.nccl_unique_id = nullptr;
+  h->dev = o->device;
+  h->P.phi = o->phi; h->P.hub_a = o->huber_delta; h->P.hub_b = o->huber_delta * o->huber_delta;
+  h->N = g->n_poses; h->E = g->n_edges; h->fixed = g->fixed_pose;
+  h->rank = o->rank; h->world = std::max(1, o->world);
+  if (h->rank < 0 || h->rank >= h->world) { g_err = "dcs_create: bad rank"; return DCS_ERR_ARG; }
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  cudaStream_t st = h->stream;
+
+  if (h->world > 1) {
+    if (!o->nccl_unique_id) { g_err = "dcs_create: world > 1 needs nccl_unique_id"; return DCS_ERR_ARG; }
+    if (!nccl_api().load()) { g_err = "libnccl.so.2 not found"; return DCS_ERR_NCCL; }
+    ncclUniqueId id;
+    std::memcpy(&id, o->nccl_unique_id, sizeof(id));
+    CKN(nccl_api().CommInitRank(&h->comm, h->world, id, h->rank));
+  }
+
+  // contiguous pose ranges, equal-sized (multiple of the CTA row tile) so in-place all-gathers work
+  const int32_t N = h->N, E = h->E;
+  const int64_t tile = (int64_t)kRowsPerBlock * h->world;
+  h->Npad = (int32_t)(((int64_t)N + tile - 1) / tile * tile);
+  h->rows_per_rank = h->Npad / h->world;
+  h->row_lo = h->rank * h->rows_per_rank;
+  h->nrows = std::max(0, std::min(N, h->row_lo + h->rows_per_rank) - h->row_lo);
+  h->nblk = std::max(1, h->rows_per_rank / kRowsPerBlock);
+  h->ldn = (int64_t)h->nblk * kRowsPerBlock;
+  const int64_t epr = ((int64_t)E + h->world - 1) / h->world;
+  h->e_lo = (int32_t)std::min<int64_t>(E, epr * h->rank);
+  h->e_hi = (int32_t)std::min<int64_t>(E, epr * (h->rank + 1));
+
+  // ---- upload the graph ---------------------------------------------------------------------
+  DevBuf<double> d_meas;
+  DevBuf<uint8_t> d_kind;
+  CK(h->ea.alloc((size_t)std::max(E, 1))); CK(h->eb.alloc((size_t)std::max(E, 1)));
+  CK(d_meas.alloc((size_t)std::max(E, 1) * 3)); CK(d_kind.alloc((size_t)std::max(E, 1)));
+  if (E > 0) {
+    CK(cudaMemcpyAsync(h->ea.p, g->edge_a, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->eb.p, g->edge_b, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_meas.p, g->meas_xyt, (size_t)E * 24, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_kind.p, g->kind, (size_t)E, cudaMemcpyHostToDevice, st));
+  }
+  const size_t EE = (size_t)std::max(E, 1);
+  CK(h->e_tmx.alloc(EE)); CK(h->e_tmy.alloc(EE)); CK(h->e_thm.alloc(EE)); CK(h->e_cm.alloc(EE)); CK(h->e_sm.alloc(EE));
+  CK(h->e_dcs.alloc(EE));
+  if (E > 0) LAUNCH(k_edge_prep, cdiv(E, 256), 256, st, d_meas.p, d_kind.p, E, o->dcs_on, h->e_tmx.p, h->e_tmy.p, h->e_thm.p,
+                    h->e_cm.p, h->e_sm.p, h->e_dcs.p);
+
+  // ---- K0: half-edges, sort, CSR, jagged-diagonal re-layout ---------------------------------------
+  CK(h->deg_all.alloc_zero((size_t)h->Npad));
+  if (E > 0) LAUNCH(k_pose_degree, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->deg_all.p);
+  CK(h->is_free.alloc_zero((size_t)h->ldn));
+  if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->is_free.p);
+
+  DevBuf<int32_t> he_off;
+  CK(he_off.alloc_zero((size_t)E + 1));
+  const int32_t row_hi = h->row_lo + h->nrows;
+  if (E > 0) LAUNCH(k_halfedge_count, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->fixed, h->row_lo, row_hi, he_off.p);
+  CKS(scan_exclusive(he_off.p, (int64_t)E + 1, st));
+  int32_t nh = 0;
+  CK(cudaMemcpyAsync(&nh, he_off.p + E, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->nh = nh;
+  h->ldh = ((int64_t)std::max(nh, 1) + 31) / 32 * 32;
+  CK(h->keys.alloc((size_t)std::max(nh, 1)));
+  CK(h->vals.alloc((size_t)std::max(nh, 1)));
+  if (E > 0) LAUNCH(k_halfedge_fill, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->fixed, h->row_lo, row_hi, he_off.p, h->keys.p, h->vals.p);
+  const int nb = bits_for(std::max(N, 2));
+  CKS(radix_sort(h->keys, h->vals, nh, nb, nb, st));
+
+  CK(h->row_ptr.alloc((size_t)h->ldn + 1));
+  {
+    // rows beyond nrows (padding) get the end offset so their degree is zero
+    const int32_t rows = (int32_t)h->ldn;
+    LAUNCH(k_row_ptr, cdiv(rows + 1, 256), 256, st, h->keys.p, nh, h->row_lo, rows, h->row_ptr.p);
+  }
+  CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
+  CK(h->rp_off.alloc_zero((size_t)h->nblk + 1));
+  LAUNCH(k_jds_rank, h->nblk, kRowsPerBlock, st, h->row_ptr.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
+  CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nblk + 1, st));
+  int32_t n_rounds = 0;
+  CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nblk, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(h->round_ptr.alloc((size_t)std::max(n_rounds, 1)));
+  LAUNCH(k_jds_rounds, h->nblk, kRowsPerBlock, st, h->row_ptr.p, (int32_t)h->ldn, h->rp_off.p, h->round_ptr.p);
+  CK(h->slot.alloc((size_t)std::max(nh, 1)));
+  if (nh > 0) LAUNCH(k_jds_slot, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_ptr.p, h->rank_of.p, h->rp_off.p,
+                     h->round_ptr.p, h->slot.p);
+
+  const size_t HH = (size_t)h->ldh;
+  CK(h->h_other.alloc_zero(HH)); CK(h->h_tmx.alloc_zero(HH)); CK(h->h_tmy.alloc_zero(HH)); CK(h->h_thm.alloc_zero(HH));
+  CK(h->h_cm.alloc_zero(HH)); CK(h->h_sm.alloc_zero(HH));
+  if (nh > 0) LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
+                     h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_cm.p, h->e_sm.p, h->e_dcs.p, h->h_other.p, h->h_tmx.p,
+                     h->h_tmy.p, h->h_thm.p, h->h_cm.p, h->h_sm.p);
+
+  // unique upper pattern (parity hook)
+  CK(h->up_flag.alloc_zero((size_t)nh + 1)); CK(h->up_scan.alloc_zero((size_t)nh + 1));
+  if (nh > 0) {
+    LAUNCH(k_upper_flag, cdiv(nh, 256), 256, st, h->keys.p, nh, h->fixed, h->up_flag.p);
+    CK(cudaMemcpyAsync(h->up_scan.p, h->up_flag.p, (size_t)(nh + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    CKS(scan_exclusive(h->up_scan.p, (int64_t)nh + 1, st));
+    CK(cudaMemcpyAsync(&h->n_upper, h->up_scan.p + nh, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+
+  // ---- state --------------------------------------------------------------------------------------
+  const size_t NP = (size_t)h->Npad, LN = (size_t)h->ldn;
+  CK(h->xyt.alloc_zero(NP)); CK(h->cand_xyt.alloc_zero(NP)); CK(h->p4.alloc_zero(NP));
+  CK(h->cs.alloc_zero(NP)); CK(h->cand_cs.alloc_zero(NP));
+  CK(h->Hoff.alloc_zero(9 * HH)); CK(h->Hdiag.alloc_zero(6 * LN)); CK(h->grad.alloc_zero(3 * LN));
+  CK(h->scale.alloc_zero(3 * LN)); CK(h->lmdiag.alloc_zero(3 * LN)); CK(h->Adiag.alloc_zero(6 * LN)); CK(h->Minv.alloc_zero(6 * LN));
+  CK(h->w.alloc_zero(3 * LN)); CK(h->r.alloc_zero(3 * LN)); CK(h->q.alloc_zero(3 * LN)); CK(h->z.alloc_zero(3 * LN));
+  CK(h->lambda_tmp.alloc_zero(3 * LN)); CK(h->rhs_tmp.alloc_zero(3 * LN));
+  const size_t max_grid = (size_t)std::max<int64_t>({(int64_t)h->nblk, (int64_t)h->vec_grid(), 148 * 8});
+  CK(h->partials.alloc_zero(4 * max_grid));
+  CK(h->scal.alloc_zero(S_COUNT));
+  CK(h->tickets.alloc_zero(8));
+  CK(h->stage3.alloc_zero((size_t)N * 3));
+  CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
+  CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
+  CKS(upload_poses(h, g->pose_xyt, h->xyt.p, h->cs.p));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  guard.h = nullptr;
+  *out = h;
+  return DCS_OK;
+}
+
+int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* residuals, double* jacobians, double* psi,
+                 double* rho1, double* gradient) {
+  if (!h) return DCS_ERR_ARG;
+  CK(cudaSetDevice(h->dev));
+  if (pose_xyt) CKS(upload_poses(h, pose_xyt, h->xyt.p, h->cs.p));
+  CKS(linearize(h, h->xyt.p, h->cs.p));
+  CKS(read_scalars(h));
+  if (cost) *cost = h->h_scal[S_COST];
+  const int32_t E = h->E;
+  if ((residuals || jacobians || psi || rho1) && E > 0) {
+    DevBuf<double> dr, dj, dp, dq;
+    if (residuals) CK(dr.alloc((size_t)E * 3));
+    if (jacobians) CK(dj.alloc((size_t)E * 18));
+    if (psi) CK(dp.alloc((size_t)E));
+    if (rho1) CK(dq.alloc((size_t)E));
+    LAUNCH(k_edge_eval, cdiv(E, kEdgeThreads), kEdgeThreads, h->stream, h->xyt.p, h->cs.p, h->edgelist(), h->P, dr.p, dj.p, dp.p, dq.p);
+    if (residuals) CK(cudaMemcpyAsync(residuals, dr.p, (size_t)E * 24, cudaMemcpyDeviceToHost, h->stream));
+    if (jacobians) CK(cudaMemcpyAsync(jacobians, dj.p, (size_t)E * 144, cudaMemcpyDeviceToHost, h->stream));
+    if (psi) CK(cudaMemcpyAsync(psi, dp.p, (size_t)E * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (rho1) CK(cudaMemcpyAsync(rho1, dq.p, (size_t)E * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (gradient) {
+    std::memset(gradient, 0, (size_t)h->N * 24);
+    if (h->nrows > 0) {
+      LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->nrows, h->ldn, h->stage3.p);
+      CK(cudaMemcpyAsync(gradient + 3 * (size_t)h->row_lo, h->stage3.p, (size_t)h->nrows * 24, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  CK(cudaGetLastError());
+  return DCS_OK;
+}
+
+int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* gradient) {
+  if (!h || !pose_xyt) return DCS_ERR_ARG;
+  CK(cudaSetDevice(h->dev));
+  CKS(upload_poses(h, pose_xyt, h->xyt.p, h->cs.p));
+  CKS(linearize(h, h->xyt.p, h->cs.p));
+  if (gradient && h->nrows > 0) {
+    LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->nrows, h->ldn, h->stage3.p);
+    CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)h->nrows * 24, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CKS(read_scalars(h));
+  if (cost) *cost = h->h_scal[S_COST];
+  if (gradient) {
+    if (h->world > 1) std::memset(gradient, 0, (size_t)h->N * 24);
+    std::memcpy(gradient + 3 * (size_t)h->row_lo, h->h_pin3, (size_t)h->nrows * 24);
+  }
+  return DCS_OK;
+}
+
+int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total) {
+  if (!h || repeats <= 0) return DCS_ERR_ARG;
+  CK(cudaSetDevice(h->dev));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < repeats; ++i) CKS(linearize(h, h->xyt.p, h->cs.p));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (ms_total) *ms_total = ms;
+  CK(cudaGetLastError());
+  return DCS_OK;
+}
+
+int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost) {
+  if (!h || !cost) return DCS_ERR_ARG;
+  CK(cudaSetDevice(h->dev));
+  const double4* x = h->xyt.p; const double2* c = h->cs.p;
+  if (pose_xyt) { CKS(upload_poses(h, pose_xyt, h->cand_xyt.p, h->cand_cs.p)); x = h->cand_xyt.p; c = h->cand_cs.p; }
+  CKS(cost_only(h, x, c, S_CAND_COST));
+  CKS(read_scalars(h));
+  *cost = h->h_scal[S_CAND_COST];
+  return DCS_OK;
+}
+
+int dcs_get_pattern(dcs_handle* h, int32_t* n_block_rows, int32_t* nnzb, int32_t* row_ptr, int32_t* col_idx) {
+  if (!h) return DCS_ERR_ARG;
+  if (h->world != 1) { g_err = "dcs_get_pattern: single-rank handles only"; return DCS_ERR_ARG; }
+  CK(cudaSetDevice(h->dev));
+  std::vector<uint8_t> is_free((size_t)h->N);
+  CK(cudaMemcpy(is_free.data(), h->is_free.p, (size_t)h->N, cudaMemcpyDeviceToHost));
+  int32_t n_diag = 0;
+  for (int32_t i = 0; i < h->N; ++i) n_diag += is_free[i];
+  if (n_block_rows) *n_block_rows = h->N;
+  if (nnzb) *nnzb = n_diag + h->n_upper;
+  if (!row_ptr || !col_idx) return DCS_OK;
+  // unique upper (row,col) keys come off the device already sorted by (row, col)
+  std::vector<uint64_t> keys((size_t)h->nh);
+  std::vector<int32_t> flag((size_t)h->nh);
+  if (h->nh > 0) {
+    CK(cudaMemcpy(keys.data(), h->keys.p, (size_t)h->nh * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(flag.data(), h->up_flag.p, (size_t)h->nh * 4, cudaMemcpyDeviceToHost));
+  }
+  int32_t pos = 0;
+  size_t i = 0;
+  for (int32_t r = 0; r < h->N; ++r) {
+    row_ptr[r] = pos;
+    if (is_free[r]) col_idx[pos++] = r;
+    while (i < keys.size() && (int32_t)(keys[i] >> 32) == r) {
+      if (flag[i]) col_idx[pos++] = (int32_t)(keys[i] & 0xFFFFFFFFu);
+      ++i;
+    }
+  }
+  row_ptr[h->N] = pos;
+  return DCS_OK;
+}
+
+int dcs_get_hessian(dcs_handle* h, double* block_values) {
+  if (!h || !block_values) return DCS_ERR_ARG;
+  if (h->world != 1) { g_err = "dcs_get_hessian: single-rank handles only"; return DCS_ERR_ARG; }
+  if (!h->have_lin) { g_err = "dcs_get_hessian: nothing linearized yet"; return DCS_ERR_ARG; }
+  CK(cudaSetDevice(h->dev));
+  const int32_t N = h->N, nh = h->nh;
+  std::vector<uint8_t> is_free((size_t)N);
+  CK(cudaMemcpy(is_free.data(), h->is_free.p, (size_t)N, cudaMemcpyDeviceToHost));
+  std::vector<double> hd((size_t)6 * h->ldn), up((size_t)std::max(h->n_upper, 1) * 9);
+  CK(cudaMemcpy(hd.data(), h->Hdiag.p, hd.size() * 8, cudaMemcpyDeviceToHost));
+  std::vector<uint64_t> keys((size_t)nh);
+  std::vector<int32_t> flag((size_t)nh);
+  if (nh > 0) {
+    DevBuf<double> d_up;
+    CK(d_up.alloc_zero(up.size()));
+    LAUNCH(k_export_upper, cdiv(nh, 256), 256, h->stream, h->keys.p, h->up_scan.p, h->up_flag.p, h->slot.p, nh, h->Hoff.p, h->ldh, d_up.p);
+    CK(cudaMemcpyAsync(up.data(), d_up.p, up.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(keys.data(), h->keys.p, (size_t)nh * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(flag.data(), h->up_flag.p, (size_t)nh * 4, cudaMemcpyDeviceToHost));
+  }
+  int64_t pos = 0, u = 0;
+  size_t i = 0;
+  for (int32_t r = 0; r < N; ++r) {
+    if (is_free[r]) {
+      const double d00 = hd[0 * h->ldn + r], d01 = hd[1 * h->ldn + r], d02 = hd[2 * h->ldn + r];
+      const double d11 = hd[3 * h->ldn + r], d12 = hd[4 * h->ldn + r], d22 = hd[5 * h->ldn + r];
+      const double blk[9] = {d00, d01, d02, d01, d11, d12, d02, d12, d22};
+      std::memcpy(block_values + 9 * pos, blk, sizeof(blk));
+      ++pos;
+    }
+    while (i < keys.size() && (int32_t)(keys[i] >> 32) == r) {
+      if (flag[i]) { std::memcpy(block_values + 9 * pos, &up[9 * u], 72); ++pos; ++u; }
+      ++i;
+    }
+  }
+  return DCS_OK;
+}
+
+int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double* w, int32_t* iterations, double* rel_residual) {
+  if (!h || !rhs || !w) return DCS_ERR_ARG;
+  if (!h->have_lin) { g_err = "dcs_pcg_solve: nothing linearized yet"; return DCS_ERR_ARG; }
+  CK(cudaSetDevice(h->dev));
+  const int32_t nr = h->nrows;
+  auto up3 = [&](const double* src, double* dst_soa) -> int {
+    std::memcpy(h->h_pin3, src + 3 * (size_t)h->row_lo, (size_t)nr * 24);
+    CK(cudaMemcpyAsync(h->stage3.p, h->h_pin3, (size_t)nr * 24, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_aos_to_soa, cdiv(nr, 256), 256, h->stream, h->stage3.p, nr, h->ldn, dst_soa);
+    CK(cudaStreamSynchronize(h->stream));
+    return DCS_OK;
+  };
+  if (nr > 0) {
+    if (lambda) CKS(up3(lambda, h->lambda_tmp.p)); else CK(cudaMemsetAsync(h->lambda_tmp.p, 0, 3 * (size_t)h->ldn * 8, h->stream));
+    CKS(up3(rhs, h->rhs_tmp.p));
+  }
+  int iters = 0;
+  double rel = 0;
+  CKS(pcg_solve(h, 0.0, h->lambda_tmp.p, h->rhs_tmp.p, &iters, &rel));
+  std::memset(w, 0, (size_t)h->N * 24);
+  if (nr > 0) {
+    LAUNCH(k_soa_to_aos, cdiv(nr, 256), 256, h->stream, h->w.p, nr, h->ldn, h->stage3.p);
+    CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)nr * 24, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(w + 3 * (size_t)h->row_lo, h->h_pin3, (size_t)nr * 24);
+  }
+  if (iterations) *iterations = iters;
+  if (rel_residual) *rel_residual = rel;
+  return DCS_OK;
+}
+
+// Ceres-default trust-region Levenberg–Marquardt (TrustRegionMinimizer + LevenbergMarquardtStrategy),
+// control on the host, all arithmetic on the device.  Works in unscaled variables: with the Jacobi
+// scaling S, Ceres solves (S H S + D^2) y = S g, step = -y, delta = S step; substituting w = S y gives
+// (H + D^2 S^-2) w = g and delta = -w, and model_cost_change = w.g - w.H.w / 2.
+int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_iteration* trace, int32_t trace_cap) {
+  if (!h || !pose_xyt_inout || !sum) return DCS_ERR_ARG;
+  CK(cudaSetDevice(h->dev));
+  std::memset(sum, 0, sizeof(*sum));
+  const dcs_options& o = h->opt;
+  const double t_start = now_s();
+  h->eval_ms = 0; h->pcg_ms = 0; h->pcg_iters_total = 0;
+  cudaStream_t st = h->stream;
+  float ms = 0;
+
+  auto timed_linearize = [&](const double4* x, const double2* c) -> int {
+    CK(cudaEventRecord(h->ev0, st));
+    CKS(linearize(h, x, c));
+    CK(cudaEventRecord(h->ev1, st));
+    CKS(read_scalars(h));
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->eval_ms += ms;
+    return DCS_OK;
+  };
+
+  CKS(upload_poses(h, pose_xyt_inout, h->xyt.p, h->cs.p));
+  LAUNCH(k_xnorm, h->vec_grid(), kVecThreads, st, h->xyt.p, h->is_free.p, h->row_lo, h->nrows, h->partials.p, h->tickets.p + 5, h->scal.p);
+  CKS(allreduce_sum(h, h->scal.p + S_XSQ, 1));
+  CKS(timed_linearize(h->xyt.p, h->cs.p));
+  double x_cost = h->h_scal[S_COST];
+  double x_norm = std::sqrt(h->h_scal[S_XSQ]);
+  if (!std::isfinite(x_cost)) {
+    sum->termination_type = DCS_FAILURE;
+    std::snprintf(sum->message, sizeof(sum->message), "Initial cost is not finite.");
+    g_err = sum->message;
+    return DCS_ERR_NUMERIC;
+  }
+  LAUNCH(k_jacobi_scale, h->vec_grid(), 256, st, h->Hdiag.p, h->nrows, h->ldn, h->scale.p, o.jacobi_scaling);
+
+  int n_logged = 0;
+  double min_logged_cost = std::numeric_limits<double>::max();
+  auto log_iter = [&](const dcs_iteration& it) {
+    if (trace && n_logged < trace_cap) trace[n_logged] = it;
+    ++n_logged;
+    min_logged_cost = std::min(min_logged_cost, it.cost);
+    if (o.verbose && h->rank == 0) {
+      if (it.iteration == 0)
+        std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter  iter_time  total_time\n");
+      std::printf("% 4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", it.iteration, it.cost, it.cost_change,
+                  it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius, it.linear_solver_iterations,
+                  it.iteration_time_s, it.cumulative_time_s);
+      std::fflush(stdout);
+    }
+  };
+
+  dcs_iteration it;
+  std::memset(&it, 0, sizeof(it));
+  it.cost = x_cost;
+  it.gradient_max_norm = h->h_scal[S_GMAX];
+  it.gradient_norm = std::sqrt(h->h_scal[S_GSQ]);
+  double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  it.trust_region_radius = radius;
+  it.iteration_time_s = it.cumulative_time_s = now_s() - t_start;
+  sum->initial_cost = x_cost;
+  int invalid = 0;
+  int term = DCS_NO_CONVERGENCE;
+  const char* msg = "Maximum number of iterations reached.";
+  log_iter(it);
+  dcs_iteration prev = it;
+  // x always lives in h->xyt (accepted iterate); the candidate in h->cand_xyt; accepted -> pointer swap
+
+  if (it.gradient_max_norm <= o.gradient_tolerance) { term = DCS_CONVERGENCE; msg = "Gradient tolerance reached."; }
+  else
+  for (;;) {
+    if (prev.iteration >= o.max_num_iterations) { term = DCS_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
+    if (prev.gradient_max_norm <= o.gradient_tolerance) { term = DCS_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
+    if (radius <= o.min_trust_region_radius) { term = DCS_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
+    const double it_start = now_s();
+    std::memset(&it, 0, sizeof(it));
+    it.iteration = prev.iteration + 1;
+
+    if (!reuse_diagonal)
+      LAUNCH(k_lm_diagonal, h->vec_grid(), 256, st, h->Hdiag.p, h->scale.p, h->nrows, h->ldn, o.min_lm_diagonal, o.max_lm_diagonal, h->lmdiag.p);
+    reuse_diagonal = true;
+    int pcg_it = 0;
+    double pcg_rel = 0;
+    CKS(pcg_solve(h, 1.0 / radius, nullptr, h->grad.p, &pcg_it, &pcg_rel));
+    it.linear_solver_iterations = pcg_it;
+    it.linear_solver_residual = pcg_rel;
+
+    // model_cost_change = w.g - w.H.w / 2
+    LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, h->grad.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->partials.p,
+           h->tickets.p + 4, h->scal.p);
+    CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
+    CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
+    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->partials.p,
+           h->tickets.p + 3, h->scal.p, (int)S_WHW, 0);
+    CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
+    // candidate = x - w
+    LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->cand_xyt.p,
+           h->cand_cs.p, h->partials.p, h->tickets.p + 5, h->scal.p);
+    CKS(allreduce_sum(h, h->scal.p + S_STEP_SQ, 2));
+    CKS(allgather_rows(h, h->cand_xyt.p, sizeof(double4)));
+    CKS(allgather_rows(h, h->cand_cs.p, sizeof(double2)));
+    CK(cudaEventRecord(h->ev0, st));
+    CKS(cost_only(h, h->cand_xyt.p, h->cand_cs.p, S_CAND_COST));
+    CK(cudaEventRecord(h->ev1, st));
+    CKS(read_scalars(h));
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->eval_ms += ms;
+    const double wg = h->h_scal[S_WG], whw = h->h_scal[S_WHW];
+    const double model_cost_change = wg - 0.5 * whw;
+    const bool finite_step = std::isfinite(wg) && std::isfinite(whw) && std::isfinite(h->h_scal[S_STEP_SQ]);
+    it.step_is_valid = finite_step && model_cost_change > 0.0;
+    if (!it.step_is_valid) {
+      if (++invalid >= o.max_num_consecutive_invalid_steps) {
+        term = DCS_FAILURE; msg = "Number of consecutive invalid steps more than max_num_consecutive_invalid_steps."; break;
+      }
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      it.cost = x_cost; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
+      it.trust_region_radius = radius;
+      it.iteration_time_s = now_s() - it_start; it.cumulative_time_s = now_s() - t_start;
+      log_iter(it); prev = it; sum->num_unsuccessful_steps++;
+      continue;
+    }
+    invalid = 0;
+    double cand = h->h_scal[S_CAND_COST];
+    if (!std::isfinite(cand)) cand = std::numeric_limits<double>::max();
+    it.step_norm = std::sqrt(h->h_scal[S_STEP_SQ]);
+    it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
+    if (it.step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) {
+      term = DCS_CONVERGENCE; msg = "Parameter tolerance reached.";
+      it.cost = x_cost; it.trust_region_radius = radius;
+      it.iteration_time_s = now_s() - it_start; it.cumulative_time_s = now_s() - t_start;
+      log_iter(it); break;
+    }
+    it.cost_change = x_cost - cand;
+    if (std::fabs(it.cost_change) <= o.function_tolerance * x_cost) {
+      term = DCS_CONVERGENCE; msg = "Function tolerance reached.";
+      it.cost = x_cost; it.trust_region_radius = radius;
+      it.iteration_time_s = now_s() - it_start; it.cumulative_time_s = now_s() - t_start;
+      log_iter(it); break;
+    }
+    it.relative_decrease = (cand >= std::numeric_limits<double>::max()) ? std::numeric_limits<double>::lowest()
+                                                                          : (x_cost - cand) / model_cost_change;
+    if (it.relative_decrease > o.min_relative_decrease) {
+      std::swap(h->xyt.p, h->cand_xyt.p);
+      std::swap(h->cs.p, h->cand_cs.p);
+      x_norm = std::sqrt(h->h_scal[S_XSQ]);
+      CKS(timed_linearize(h->xyt.p, h->cs.p));
+      x_cost = h->h_scal[S_COST];
+      it.step_is_successful = 1;
+      it.cost = x_cost;
+      it.gradient_max_norm = h->h_scal[S_GMAX];
+      it.gradient_norm = std::sqrt(h->h_scal[S_GSQ]);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+      radius = std::min(o.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      sum->num_successful_steps++;
+    } else {
+      it.cost = cand;
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      sum->num_unsuccessful_steps++;
+    }
+    it.trust_region_radius = radius;
+    it.iteration_time_s = now_s() - it_start; it.cumulative_time_s = now_s() - t_start;
+    log_iter(it);
+    prev = it;
+  }
+
+  // monotonic steps: the accepted iterate in h->xyt is the best one
+  CKS(download_poses(h, h->xyt.p, pose_xyt_inout));
+  sum->final_cost = std::min(sum->initial_cost, min_logged_cost);
+  sum->num_iterations = n_logged;
+  sum->termination_type = term;
+  sum->total_pcg_iterations = h->pcg_iters_total;
+  sum->total_time_s = now_s() - t_start;
+  sum->eval_time_s = h->eval_ms * 1e-3;
+  sum->linear_solver_time_s = h->pcg_ms * 1e-3;
+  std::snprintf(sum->message, sizeof(sum->message), "%s", msg);
+  CK(cudaGetLastError());
+  return DCS_OK;
+}
+
+}  // extern "C"

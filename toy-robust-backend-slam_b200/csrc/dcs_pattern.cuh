@@ -1,0 +1,209 @@
+// dcs_pattern.cuh — K0: one-time, integer-only construction of the block structure of J^T J.
+//
+// Replaces what Ceres does once per solve for SPARSE_NORMAL_CHOLESKY (reference call site
+// DCS-ceres/main.cpp:156): enumerate the per-residual block pairs, sort them, build the
+// compressed structure.  Here: every edge (a,b) yields two half-edges (row=a,col=b) and
+// (row=b,col=a) (only for non-constant rows); a hand-written stable LSD radix sort orders them
+// by (row, col); the sorted list is (i) the full-storage block CSR the SpMV walks and (ii) after
+// a flag+scan unique, the upper-triangular block pattern {(i,i)} U {(min,max)} that the parity
+// hook exports.  The CSR is then re-laid per CTA of 128 rows in jagged-diagonal order so that a
+// thread-per-row kernel reads it fully coalesced with no padding.
+#pragma once
+#include "dcs_common.cuh"
+
+namespace dcs {
+
+// ---- exclusive scan (int32), in place; recursion on block totals --------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void k_scan_tile(int32_t* data, int64_t n, int32_t* totals) {
+  __shared__ int32_t s_warp[kScanThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int32_t v[kScanItems];
+  int32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { v[i] = (base + i < n) ? data[base + i] : 0; sum += v[i]; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int32_t w = (lane < kScanThreads / 32) ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < kScanThreads / 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    if (lane < kScanThreads / 32) s_warp[lane] = w;
+  }
+  __syncthreads();
+  int32_t excl = incl - sum + (wid > 0 ? s_warp[wid - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { if (base + i < n) data[base + i] = excl; excl += v[i]; }
+  if (threadIdx.x == kScanThreads - 1) totals[blockIdx.x] = excl;
+}
+
+__global__ void k_scan_add(int32_t* data, int64_t n, const int32_t* totals) {
+  const int64_t i = (int64_t)blockIdx.x * kScanTile + threadIdx.x;
+  const int32_t off = totals[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { const int64_t j = i + (int64_t)k * kScanThreads; if (j < n) data[j] += off; }
+}
+
+// ---- radix sort pass: 8-bit digit, stable ----------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+__global__ void k_radix_hist(const uint64_t* keys, int64_t n, int shift, int32_t* hist, int nblk) {
+  __shared__ int32_t s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int c = 0; c < kSortItems; ++c) {
+    const int64_t i = base + (int64_t)c * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 0xFF], 1);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = s_h[threadIdx.x];   // digit-major
+}
+
+__global__ void k_radix_scatter(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out,
+                                uint32_t* vals_out, int64_t n, int shift, const int32_t* hist, int nblk) {
+  __shared__ int32_t s_run[256];
+  __shared__ int32_t s_wcnt[kSortThreads / 32][256];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  s_run[threadIdx.x] = hist[(int64_t)threadIdx.x * nblk + blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < kSortThreads / 32; ++w) s_wcnt[w][threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  for (int c = 0; c < kSortItems; ++c) {
+    const int64_t i = base + (int64_t)c * kSortThreads + threadIdx.x;
+    const bool valid = i < n;
+    uint64_t key = 0; uint32_t val = 0;
+    if (valid) { key = keys_in[i]; val = vals_in[i]; }
+    const unsigned int d = valid ? (unsigned int)((key >> shift) & 0xFF) : 256u + lane;  // invalid: unique class
+    const unsigned int peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wcnt[wid][d] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      int off = s_run[d] + rank;
+      for (int w = 0; w < wid; ++w) off += s_wcnt[w][d];
+      keys_out[off] = key;
+      vals_out[off] = val;
+    }
+    __syncthreads();
+    {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < kSortThreads / 32; ++w) { t += s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = 0; }
+      s_run[threadIdx.x] += t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- half-edge generation ---------------------------------------------------------------------
+// key = row << 32 | col; val = edge << 1 | side.  Rows outside [row_lo,row_hi) or constant rows
+// are not generated (count pass with out == nullptr, then fill pass with offsets).
+__global__ void k_halfedge_count(const int32_t* ea, const int32_t* eb, int32_t E, int32_t fixed, int32_t row_lo,
+                                 int32_t row_hi, int32_t* cnt) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int32_t a = ea[e], b = eb[e];
+  int c = 0;
+  if (a != fixed && a >= row_lo && a < row_hi) ++c;
+  if (b != fixed && b >= row_lo && b < row_hi) ++c;
+  cnt[e] = c;
+}
+__global__ void k_halfedge_fill(const int32_t* ea, const int32_t* eb, int32_t E, int32_t fixed, int32_t row_lo,
+                                int32_t row_hi, const int32_t* off, uint64_t* keys, uint32_t* vals) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int32_t a = ea[e], b = eb[e];
+  int32_t o = off[e];
+  if (a != fixed && a >= row_lo && a < row_hi) { keys[o] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; vals[o] = ((uint32_t)e << 1); ++o; }
+  if (b != fixed && b >= row_lo && b < row_hi) { keys[o] = ((uint64_t)(uint32_t)b << 32) | (uint32_t)a; vals[o] = ((uint32_t)e << 1) | 1u; }
+}
+
+// degree of every pose over ALL edges (decides which poses are parameters at all)
+__global__ void k_pose_degree(const int32_t* ea, const int32_t* eb, int32_t E, int32_t* deg) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  atomicAdd(&deg[ea[e]], 1);
+  atomicAdd(&deg[eb[e]], 1);
+}
+
+// row_ptr[r - row_lo] = first sorted half-edge whose row >= r   (r in [row_lo, row_hi]); binary search
+__global__ void k_row_ptr(const uint64_t* keys, int32_t nh, int32_t row_lo, int32_t nrows, int32_t* row_ptr) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nrows) return;
+  const uint64_t target = (uint64_t)(uint32_t)(row_lo + r) << 32;
+  int32_t lo = 0, hi = nh;
+  while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+  row_ptr[r] = lo;
+}
+
+// ---- jagged-diagonal re-layout per CTA of kRowsPerBlock rows -------------------------------------
+// pass 1: rank of each row inside its CTA by decreasing degree (stable), max degree per CTA
+__global__ void k_jds_rank(const int32_t* row_ptr, int32_t nrows, uint8_t* rank_of, uint8_t* perm, int32_t* blk_rounds) {
+  __shared__ int32_t s_deg[kRowsPerBlock];
+  const int32_t r = blockIdx.x * kRowsPerBlock + threadIdx.x;
+  const int32_t d = (r < nrows) ? row_ptr[r + 1] - row_ptr[r] : 0;
+  s_deg[threadIdx.x] = d;
+  __syncthreads();
+  int rank = 0;
+  for (int u = 0; u < kRowsPerBlock; ++u) {
+    const int32_t du = s_deg[u];
+    rank += (du > d) || (du == d && u < (int)threadIdx.x);
+  }
+  rank_of[(int64_t)blockIdx.x * kRowsPerBlock + threadIdx.x] = (uint8_t)rank;
+  perm[(int64_t)blockIdx.x * kRowsPerBlock + rank] = (uint8_t)threadIdx.x;
+  if (rank == 0) blk_rounds[blockIdx.x] = d + 1;   // rounds + 1 entries in round_ptr
+}
+// pass 2: round_ptr[rp_off[b] + k] = first JDS slot of round k of CTA b
+__global__ void k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32_t* round_ptr) {
+  __shared__ int32_t s_deg[kRowsPerBlock];
+  const int32_t r0 = blockIdx.x * kRowsPerBlock;
+  const int32_t r = r0 + threadIdx.x;
+  s_deg[threadIdx.x] = (r < nrows) ? row_ptr[r + 1] - row_ptr[r] : 0;
+  __syncthreads();
+  int32_t maxd = 0;
+  for (int u = 0; u < kRowsPerBlock; ++u) maxd = max(maxd, s_deg[u]);
+  const int32_t base = row_ptr[min(r0, nrows)];
+  const int32_t off = rp_off[blockIdx.x];
+  // round k starts after sum_{u<k} #{rows with deg > u} = sum_rows min(deg, k)
+  for (int32_t k = threadIdx.x; k <= maxd; k += kRowsPerBlock) {
+    int32_t s = 0;
+    for (int u = 0; u < kRowsPerBlock; ++u) s += min(s_deg[u], k);
+    round_ptr[off + k] = base + s;
+  }
+}
+// pass 3: sorted CSR position -> JDS slot
+__global__ void k_jds_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, const int32_t* row_ptr,
+                           const uint8_t* rank_of, const int32_t* rp_off, const int32_t* round_ptr, int32_t* slot) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int32_t r = (int32_t)(keys[i] >> 32) - row_lo;
+  const int32_t k = i - row_ptr[r];
+  const int32_t b = r / kRowsPerBlock;
+  slot[i] = round_ptr[rp_off[b] + k] + rank_of[r];
+}
+
+// ---- unique upper pattern (parity hook) ------------------------------------------------------------
+// flag[i] = 1 for the first sorted half-edge of every distinct (row,col) with row < col and col not
+// constant.  (Diagonal entries are added per non-empty row by the caller.)
+__global__ void k_upper_flag(const uint64_t* keys, int32_t nh, int32_t fixed, int32_t* flag) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const uint64_t k = keys[i];
+  const int32_t row = (int32_t)(k >> 32), col = (int32_t)(k & 0xFFFFFFFFu);
+  const bool first = (i == 0) || (keys[i - 1] != k);
+  flag[i] = (first && row < col && col != fixed) ? 1 : 0;
+}
+
+}  // namespace dcs
