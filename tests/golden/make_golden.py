@@ -1,0 +1,88 @@
+"""Generates tests/golden/*.npz (run in the build container, where /root/reference exists).
+
+Inputs  : the six g2o datasets of the reference (DCS-ceres/data/*.g2o), read by this repo's C++
+          reader, outliers injected by its add_random_C with srand(1) (glibc rand()).
+Outputs : * per-edge residuals and 3x6 Jacobians from the REFERENCE's own functors
+            (DCS-ceres/src/ceres_error.cpp compiled where it lies against oracle/ref_shim/ ->
+            oracle/_ref/libdcs_ref.so), at the file's poses and at one perturbed pose set,
+            DCS on and off;
+          * the oracle's (oracle/dcs_oracle.cpp) costs, LM traces and final poses — the LM part
+            is a restatement of Ceres semantics (Ceres itself is absent offline: parity unpinned);
+          * structural known-answers.
+The fixtures are small, committed, and carry their inputs so the GPU box needs no dataset."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "toy-robust-backend-slam_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from dcs_b200 import Graph  # noqa: E402
+import oracle_py as O  # noqa: E402
+
+DATA = "/root/reference/DCS-ceres/data"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def trace_arrays(tr):
+    return dict(cost=np.array([t.cost for t in tr]), radius=np.array([t.trust_region_radius for t in tr]),
+                ok=np.array([t.step_is_successful for t in tr], np.int8),
+                gmax=np.array([t.gradient_max_norm for t in tr]), step=np.array([t.step_norm for t in tr]),
+                rho=np.array([t.relative_decrease for t in tr]))
+
+
+def solve_case(name, n_bogus):
+    g = Graph.from_g2o(f"{DATA}/{name}.g2o", n_bogus, seed=1)
+    rng = np.random.default_rng(7)
+    xp = g.pose_xyt + rng.normal(0, 0.05, g.pose_xyt.shape)
+    xp[g.fixed_pose] = g.pose_xyt[g.fixed_pose]
+    extra = dict(pose_perturbed=xp, counts=np.array(g.counts, np.int32))
+    for dcs in (1, 0):
+        kind = ((g.kind != 0) & bool(dcs)).astype(np.uint8)
+        for tag, x in (("init", g.pose_xyt), ("pert", xp)):
+            e, J = O.ref_edges(kind, g.meas_xyt, x[g.edge_a], x[g.edge_b])
+            extra[f"ref_e_{tag}_dcs{dcs}"] = e
+            extra[f"ref_J_{tag}_dcs{dcs}"] = J
+        ora = O.Oracle(g, dcs_on=bool(dcs))
+        ev = ora.evaluate()
+        x, s, tr = ora.solve()
+        extra[f"cost_init_dcs{dcs}"] = ev["cost"]
+        extra[f"final_cost_dcs{dcs}"] = s.final_cost
+        extra[f"final_pose_dcs{dcs}"] = x
+        extra[f"termination_dcs{dcs}"] = s.termination_type
+        for k, v in trace_arrays(tr).items():
+            extra[f"trace_{k}_dcs{dcs}"] = v
+        fin = ora.evaluate(x)
+        extra[f"final_psi_dcs{dcs}"] = fin["psi"]
+        print(name, n_bogus, "dcs", dcs, "cost", ev["cost"], "->", s.final_cost, "iters", s.num_iterations,
+              "ok", s.num_successful_steps, s.message.decode())
+    g.save_npz(f"{OUT}/{name}_{n_bogus}_seed1.npz", **extra)
+
+
+def structure():
+    out = {}
+    for name in ("CSAIL", "FR079", "FRH", "INTEL", "M3500", "MIT"):
+        g = Graph.from_g2o(f"{DATA}/{name}.g2o", 0)
+        a, b = g.edge_a.astype(np.int64), g.edge_b.astype(np.int64)
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        pairs = np.unique(lo * g.n_poses + hi)
+        upper = np.unique((lo * g.n_poses + hi)[(lo != 0)])
+        deg = np.bincount(np.concatenate([a, b]), minlength=g.n_poses)
+        rp, ci = O.Oracle(g).pattern()
+        out[name] = dict(n_poses=g.n_poses, n_edges=g.n_edges, n_odometry=int(g.counts[1]), n_closure=int(g.counts[2]),
+                         unique_pairs=int(pairs.size), upper_offdiag=int(upper.size), max_degree=int(deg.max()),
+                         diag_blocks=int((deg[1:] > 0).sum()), nnzb=int(ci.size))
+        np.savez_compressed(f"{OUT}/{name}_edges.npz", edge_a=g.edge_a, edge_b=g.edge_b, n_poses=g.n_poses,
+                            row_ptr=rp, col_idx=ci)
+        print(name, out[name])
+    json.dump(out, open(f"{OUT}/structure.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    assert O.ref_lib() is not None, "build oracle/_ref first (make -C oracle ref)"
+    structure()
+    solve_case("INTEL", 50)
+    solve_case("INTEL", 0)
+    solve_case("M3500", 100)
