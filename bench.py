@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DCS-LM hot path (BASELINE.json: edges/s of residual+Jacobian
+evaluation fused with J^T J / J^T r assembly, on the synthetic 1M-pose / 4M-edge graph with 10% outlier loops).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU implementation of the same path (oracle port,
+                                                           # all host threads), rank 0 only
+
+One step = one pass of the fused eval+assembly kernel over the rank's rows.  N>1: one process per GPU (torchrun),
+contiguous pose ranges per rank, 1M poses per rank (weak scaling), cost / gradient-norm scalars combined with
+NCCL all-reduce inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "toy-robust-backend-slam_b200"))
+
+POSES_PER_GPU = 1_000_000
+LOOPS_PER_GPU = 2_700_001 - 0      # + 999 999 odometry + 300 000 outliers = 4 000 000 edges per 1M poses
+OUTLIERS_PER_GPU = 300_000
+CPU_SAMPLE_POSES = 250_000          # bounded sample of the same generator for the CPU arm
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                               "-i", str(self.index)], timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples and self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+_CPU = {}
+
+
+def cpu_arm(threads, budget_s=12.0):
+    """Oracle port (oracle/dcs_oracle.cpp: Jet evaluation of the reference functors + J^T J / J^T r) timed on the host
+    cores over a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    from dcs_b200 import Graph
+    n = CPU_SAMPLE_POSES
+    if "ora" not in _CPU:
+        _CPU["g"] = Graph.synthetic(n, int(2.700001 * n), n_bogus=int(0.3 * n))
+        _CPU["ora"] = O.Oracle(_CPU["g"], dcs_on=True, num_threads=threads)
+    g, ora = _CPU["g"], _CPU["ora"]
+    t1 = ora.time_linearize(1)
+    reps = max(1, min(200, int(budget_s / max(t1, 1e-6))))
+    t = ora.time_linearize(reps)
+    return {"value": g.n_edges / t, "unit": "edges/s", "cores": threads, "kind": "port",
+            "sample": f"synthetic Manhattan {n} poses / {g.n_edges} edges (same generator, 10% outlier loops), "
+                      f"{reps} passes of Jet eval + JtJ/Jtr assembly, {t * 1e3:.1f} ms/pass"}, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lm-iters", type=int, default=2, help="LM iterations of the full-solve side measurement (0 = skip)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(3, a.warmup)
+    workload = (f"synthetic 2D Manhattan grid, {POSES_PER_GPU} poses / 4000000 edges per GPU, 10% outlier loops, DCS on "
+                f"(phi=0.5), Huber(0.01); BASELINE.json configs[3]")
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        t0 = time.time()
+        per_step = []
+        cb = None
+        for i in range(warmup + a.steps):
+            cb, t = cpu_arm(threads, budget_s=max(1.0, 60.0 / (warmup + a.steps)))
+            if i >= warmup:
+                per_step.append(t)
+        v = cb["value"]
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "edges_per_sec_eval_assembly", "value": v, "unit": "edges/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": warmup, "ms_per_step": 1e3 * sum(per_step) / len(per_step),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": workload, "cpu_sample": cb["sample"]},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "wall_s": time.time() - t0}))
+        return
+
+    import numpy as np
+    import dcs_b200 as D
+    dist = None
+    uid = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = torch.frombuffer(bytearray(D.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    n_poses = POSES_PER_GPU * world
+    g = D.Graph.synthetic(n_poses, LOOPS_PER_GPU * world - (world - 1), n_bogus=OUTLIERS_PER_GPU * world)
+    opts = dict(device=local_rank, rank=rank, world=world)
+    if uid:
+        opts["nccl_unique_id"] = uid
+    t_create = time.time()
+    s = D.Solver(g, dcs_on=True, **opts)
+    t_create = time.time() - t_create
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    # ---- device-resident metric: K steps of the fused eval+assembly launch, CUDA events on the library's stream
+    s.linearize_resident(warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    D.launch_count(reset=True)
+    ms = s.linearize_resident(a.steps)
+    launches = D.launch_count()
+    barrier()
+    if dist:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = ms / a.steps
+    value = g.n_edges / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the C-ABI with host buffers: H2D poses, launch, D2H cost + gradient, every step
+    x = np.array(g.pose_xyt)
+    for _ in range(3):
+        s.linearize(x)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cost, grad = s.linearize(x)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if dist:
+        import torch
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.summary()
+    e2e_value = g.n_edges / (e2e_s / a.steps)
+    rows_local = POSES_PER_GPU
+    h2d = n_poses * 24
+    d2h = rows_local * 24 + 16 * 8
+
+    # ---- roofline of the dominant kernel (k_linearize): algorithmic bytes 108 E + 120 N per launch (per rank)
+    peak, peak_src = peaks()
+    e_local = g.n_edges / world
+    alg_bytes = 108.0 * e_local + 120.0 * rows_local
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "linearize_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes}
+
+    # ---- side measurement: bounded full DCS-LM solve on the same graph (LM iterations/s, PCG iterations/s)
+    lm = None
+    if a.lm_iters > 0:
+        s.close()
+        s = D.Solver(g, dcs_on=True, max_num_iterations=a.lm_iters, pcg_rel_tol=1e-8, pcg_max_iter=3000, **opts)
+        t0 = time.perf_counter()
+        xs, summ, trace = s.solve()
+        dt = time.perf_counter() - t0
+        lm = {"lm_iterations": summ.num_iterations - 1, "seconds": dt, "lm_iters_per_sec": (summ.num_iterations - 1) / dt,
+              "pcg_iterations": int(summ.total_pcg_iterations), "pcg_rel_tol": 1e-8,
+              "us_per_pcg_iteration": 1e6 * summ.linear_solver_time_s / max(1, summ.total_pcg_iterations),
+              "initial_cost": summ.initial_cost, "final_cost": summ.final_cost}
+    s.close()
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cb, _ = cpu_arm(os.cpu_count() or 1)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "edges_per_sec_eval_assembly", "value": value, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "n_poses": n_poses, "n_edges": g.n_edges, "partition": f"pose-range x{world}",
+                   "l2": "inputs larger than L2 (352 MB half-edge stream + 0.7 GB block output per launch)",
+                   "create_s": t_create},
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / a.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb, "lm": lm,
+        "final_cost_check": cost}))
+
+
+if __name__ == "__main__":
+    main()

@@ -98,26 +98,46 @@ __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32
                                  int32_t nh, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                  const int32_t* __restrict__ deg_all, int32_t fixed, const double* __restrict__ tmx,
                                  const double* __restrict__ tmy, const double* __restrict__ thm, const double* __restrict__ cm,
-                                 const double* __restrict__ sm, const uint8_t* __restrict__ dcs_flag, uint32_t* h_other,
-                                 double* h_tmx, double* h_tmy, double* h_thm, double* h_cm, double* h_sm) {
+                                 const double* __restrict__ sm, const uint8_t* __restrict__ dcs_flag, int32_t row_lo, int32_t row_hi,
+                                 uint32_t* h_other, double* h_tmx, double* h_tmy, double* h_thm, double* h_cm, double* h_sm,
+                                 int32_t* edge_slot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const uint32_t v = vals[i];
   const int32_t e = (int32_t)(v >> 1);
   const bool side_b = (v & 1u) != 0;
   const int32_t other = (int32_t)(keys[i] & 0xFFFFFFFFu);
+  const int32_t row = (int32_t)(keys[i] >> 32);
   const int32_t a = ea[e];
   uint32_t word = (uint32_t)other;
   if (side_b) word |= kFlagSideB;
   if (dcs_flag[e]) word |= kFlagDcs;
   if (other == fixed) word |= kFlagOtherFixed;
+  // upper-triangular owner; blocks whose partner row lives on another rank are written on both ranks
+  else if (row < other || other < row_lo || other >= row_hi) word |= kFlagOwner;
   // the edge's cost is booked on its a-side half-edge, or on the b side when a is constant
   const bool a_has_row = (a != fixed);
   if ((!side_b && a_has_row) || (side_b && !a_has_row)) word |= kFlagCost;
   const int32_t s = slot[i];
   h_other[s] = word;
   h_tmx[s] = tmx[e]; h_tmy[s] = tmy[e]; h_thm[s] = thm[e]; h_cm[s] = cm[e]; h_sm[s] = sm[e];
+  edge_slot[2 * (int64_t)e + (side_b ? 1 : 0)] = s;
   (void)deg_all; (void)eb;
+}
+
+// mirror_src[slot]: slot of the partner half-edge whose (owner) block this slot mirrors, or -1
+__global__ void k_mirror_src(const uint32_t* __restrict__ vals, const int32_t* __restrict__ slot, int32_t nh,
+                             const uint32_t* __restrict__ h_other, const int32_t* __restrict__ edge_slot, int32_t* mirror_src) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int32_t s = slot[i];
+  const uint32_t word = h_other[s];
+  int32_t src = -1;
+  if (!(word & kFlagOwner) && !(word & kFlagOtherFixed)) {
+    const uint32_t v = vals[i];
+    src = edge_slot[2 * (int64_t)(v >> 1) + ((v & 1u) ^ 1u)];
+  }
+  mirror_src[s] = src;
 }
 
 __global__ void k_is_free(const int32_t* __restrict__ deg_all, int32_t row_lo, int32_t nrows, int32_t fixed, uint8_t* is_free) {
@@ -159,7 +179,7 @@ struct dcs_handle {
   ncclComm_t comm = nullptr;
   int32_t rows_per_rank = 0, row_lo = 0, nrows = 0, Npad = 0;
   int32_t e_lo = 0, e_hi = 0;
-  int32_t nblk = 0, nh = 0;
+  int32_t nblk = 0, nh = 0, nwin = 0, ntasks = 0;
   int64_t ldn = 0, ldh = 0;
   // graph (device)
   DevBuf<int32_t> ea, eb, deg_all;
@@ -168,8 +188,9 @@ struct dcs_handle {
   // pattern
   DevBuf<uint64_t> keys;        // sorted (row<<32|col)
   DevBuf<uint32_t> vals;        // edge<<1|side
-  DevBuf<int32_t> row_ptr, rp_off, round_ptr, slot, up_flag, up_scan;
-  DevBuf<uint8_t> rank_of, perm;
+  DevBuf<int32_t> row_ptr, rp_off, round_ptr, slot, up_flag, up_scan, mirror_src;
+  bool mirrored = false;       // lower copies of Hoff are current
+  DevBuf<uint16_t> rank_of, perm;
   int32_t n_upper = 0;
   // half-edges (JDS order)
   DevBuf<uint32_t> h_other;
@@ -179,6 +200,8 @@ struct dcs_handle {
   DevBuf<double2> cs, cand_cs;
   DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
   DevBuf<double> partials, scal, stage3;   // stage3: N x 3 staging for host<->device AoS
+  DevBuf<double> red_part, red_gpart;      // warp_grid_reduce workspace (row-owner kernels)
+  DevBuf<unsigned int> red_tickets;        // [ngroups] group tickets + [1] global ticket
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
@@ -193,6 +216,7 @@ struct dcs_handle {
     RowLayout L;
     L.row_lo = row_lo; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;
     L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
+    L.nwin = nwin; L.ntasks = ntasks;
     return L;
   }
   HalfEdges halfedges() const {
@@ -206,6 +230,11 @@ struct dcs_handle {
     return L;
   }
   int vec_grid() const { return std::max(1, cdiv(nrows, kVecThreads)); }
+  WarpRedWs red() const {
+    WarpRedWs w;
+    w.part = red_part.p; w.gpart = red_gpart.p; w.gticket = red_tickets.p; w.ticket = red_tickets.p + cdiv(nblk, kRedGroup);
+    return w;
+  }
 };
 
 namespace {
@@ -300,10 +329,19 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 // K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
 int linearize(dcs_handle* h, const double4* xyt, const double2* cs) {
   LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, cs, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
-         h->grad.p, h->partials.p, h->tickets.p, h->scal.p);
+         h->grad.p, h->red(), h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_COST, 2));
   CKS(allreduce_max(h, h->scal.p + S_GMAX, 1));
   h->have_lin = true;
+  h->mirrored = false;
+  return DCS_OK;
+}
+
+// linear-solver setup: fill the lower (mirrored) block copies the row-wise SpMV reads
+int ensure_mirror(dcs_handle* h) {
+  if (h->mirrored || h->nh == 0) { h->mirrored = true; return DCS_OK; }
+  LAUNCH(k_mirror, cdiv(h->nh, 256), 256, h->stream, h->mirror_src.p, h->nh, h->ldh, h->Hoff.p);
+  h->mirrored = true;
   return DCS_OK;
 }
 
@@ -318,8 +356,8 @@ int cost_only(dcs_handle* h, const double4* xyt, const double2* cs, int slot) {
 
 // one PCG iteration on the stream (capturable)
 int pcg_iteration(dcs_handle* h, const double* D) {
-  LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->partials.p,
-         h->tickets.p + 3, h->scal.p, (int)S_PQ, 1);
+  LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->red(),
+         h->scal.p, (int)S_PQ, 1);
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
   LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, h->row_lo, h->nrows, h->ldn, h->w.p,
          h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
@@ -333,6 +371,7 @@ int pcg_iteration(dcs_handle* h, const double* D) {
 int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, const double* rhs, int* iters_out,
               double* relres_out) {
   CK(cudaEventRecord(h->ev0, h->stream));
+  CKS(ensure_mirror(h));
   LAUNCH(k_precond, h->vec_grid(), 256, h->stream, h->Hdiag.p, h->lmdiag.p, h->scale.p, h->is_free.p, h->nrows, h->ldn, inv_radius,
          lambda_explicit, h->Adiag.p, h->Minv.p);
   LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->w.p, h->r.p,
@@ -487,13 +526,15 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
 
   // contiguous pose ranges, equal-sized (multiple of the CTA row tile) so in-place all-gathers work
   const int32_t N = h->N, E = h->E;
-  const int64_t tile = (int64_t)kRowsPerBlock * h->world;
+  const int64_t tile = (int64_t)kWindow * h->world;
   h->Npad = (int32_t)(((int64_t)N + tile - 1) / tile * tile);
   h->rows_per_rank = h->Npad / h->world;
   h->row_lo = h->rank * h->rows_per_rank;
   h->nrows = std::max(0, std::min(N, h->row_lo + h->rows_per_rank) - h->row_lo);
-  h->nblk = std::max(1, h->rows_per_rank / kRowsPerBlock);
-  h->ldn = (int64_t)h->nblk * kRowsPerBlock;
+  h->nwin = std::max(1, h->rows_per_rank / kWindow);
+  h->ntasks = h->nwin * kSlicesPerWindow;
+  h->nblk = h->ntasks;                                // CTAs of the row-owner kernels (one warp task each)
+  h->ldn = (int64_t)h->nwin * kWindow;
   const int64_t epr = ((int64_t)E + h->world - 1) / h->world;
   h->e_lo = (int32_t)std::min<int64_t>(E, epr * h->rank);
   h->e_hi = (int32_t)std::min<int64_t>(E, epr * (h->rank + 1));
@@ -544,14 +585,14 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     LAUNCH(k_row_ptr, cdiv(rows + 1, 256), 256, st, h->keys.p, nh, h->row_lo, rows, h->row_ptr.p);
   }
   CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
-  CK(h->rp_off.alloc_zero((size_t)h->nblk + 1));
-  LAUNCH(k_jds_rank, h->nblk, kRowsPerBlock, st, h->row_ptr.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
-  CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nblk + 1, st));
+  CK(h->rp_off.alloc_zero((size_t)h->nwin + 1));
+  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
+  CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nwin + 1, st));
   int32_t n_rounds = 0;
-  CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nblk, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nwin, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(h->round_ptr.alloc((size_t)std::max(n_rounds, 1)));
-  LAUNCH(k_jds_rounds, h->nblk, kRowsPerBlock, st, h->row_ptr.p, (int32_t)h->ldn, h->rp_off.p, h->round_ptr.p);
+  LAUNCH(k_jds_rounds, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rp_off.p, h->round_ptr.p);
   CK(h->slot.alloc((size_t)std::max(nh, 1)));
   if (nh > 0) LAUNCH(k_jds_slot, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_ptr.p, h->rank_of.p, h->rp_off.p,
                      h->round_ptr.p, h->slot.p);
@@ -559,9 +600,17 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const size_t HH = (size_t)h->ldh;
   CK(h->h_other.alloc_zero(HH)); CK(h->h_tmx.alloc_zero(HH)); CK(h->h_tmy.alloc_zero(HH)); CK(h->h_thm.alloc_zero(HH));
   CK(h->h_cm.alloc_zero(HH)); CK(h->h_sm.alloc_zero(HH));
-  if (nh > 0) LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
-                     h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_cm.p, h->e_sm.p, h->e_dcs.p, h->h_other.p, h->h_tmx.p,
-                     h->h_tmy.p, h->h_thm.p, h->h_cm.p, h->h_sm.p);
+  CK(h->mirror_src.alloc((size_t)std::max(nh, 1)));
+  if (nh > 0) {
+    DevBuf<int32_t> edge_slot;
+    CK(edge_slot.alloc((size_t)2 * EE));
+    CK(cudaMemsetAsync(edge_slot.p, 0xFF, (size_t)2 * EE * 4, st));
+    LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
+           h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_cm.p, h->e_sm.p, h->e_dcs.p, h->row_lo, row_hi, h->h_other.p,
+           h->h_tmx.p, h->h_tmy.p, h->h_thm.p, h->h_cm.p, h->h_sm.p, edge_slot.p);
+    LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, h->mirror_src.p);
+    CK(cudaStreamSynchronize(st));
+  }
 
   // unique upper pattern (parity hook)
   CK(h->up_flag.alloc_zero((size_t)nh + 1)); CK(h->up_scan.alloc_zero((size_t)nh + 1));
@@ -585,6 +634,9 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->partials.alloc_zero(4 * max_grid));
   CK(h->scal.alloc_zero(S_COUNT));
   CK(h->tickets.alloc_zero(8));
+  CK(h->red_part.alloc_zero((size_t)3 * h->nblk));
+  CK(h->red_gpart.alloc_zero((size_t)3 * cdiv(h->nblk, kRedGroup)));
+  CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1));
   CK(h->stage3.alloc_zero((size_t)N * 3));
   CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
@@ -870,8 +922,9 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
            h->tickets.p + 4, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
     CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
-    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->partials.p,
-           h->tickets.p + 3, h->scal.p, (int)S_WHW, 0);
+    CKS(ensure_mirror(h));
+    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->red(),
+           h->scal.p, (int)S_WHW, 0);
     CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
     // candidate = x - w
     LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->cand_xyt.p,

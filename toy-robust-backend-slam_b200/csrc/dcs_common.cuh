@@ -10,12 +10,18 @@ namespace dcs {
 // ------------------------------------------------------------------------------------------
 // layout constants
 // ------------------------------------------------------------------------------------------
-constexpr int kRowsPerBlock = 128;       // rows (poses) per CTA in the row-owner kernels
-constexpr uint32_t kIdxMask = 0x0FFFFFFFu;  // low 28 bits of a half-edge word: other pose
+constexpr int kRowsPerBlock = 32;        // threads per CTA in the row-owner kernels: ONE warp task per CTA, so a
+                                         // finished task frees its registers at once (no sibling warp to wait for)
+constexpr int kWindow = 1024;            // rows per jagged-diagonal window (sorted by degree inside it)
+constexpr int kSlice = 32;               // rows per warp task
+constexpr int kSlicesPerWindow = kWindow / kSlice;
+constexpr uint32_t kIdxMask = 0x07FFFFFFu;  // low 27 bits of a half-edge word: other pose (<= 134M poses)
 constexpr uint32_t kFlagSideB = 1u << 31;   // row pose is the edge's second endpoint (Edge::b)
 constexpr uint32_t kFlagDcs = 1u << 30;     // DCS functor applies (loop/bogus edge and METHOD 1)
 constexpr uint32_t kFlagOtherFixed = 1u << 29;  // other endpoint is constant: no off-diagonal block
 constexpr uint32_t kFlagCost = 1u << 28;    // this half-edge accounts for the edge's cost
+constexpr uint32_t kFlagOwner = 1u << 27;   // this half-edge writes the edge's off-diagonal block (upper triangle, or a
+                                            // block whose mirror lives on another rank)
 
 struct Params {
   double phi;       // DCS upper bound (0.5)
@@ -112,21 +118,175 @@ __device__ __forceinline__ void edge_linearize(double xa, double ya, double tha,
 }
 
 // ------------------------------------------------------------------------------------------
+// Normal-equation terms of one edge WITHOUT forming the Jacobian (hot path, k_linearize).
+//
+// With A0 = [[-Q, t],[0, -sigma]], B0 = [[Q, 0],[0, sigma]] the plain Jacobians (Q = Rm^T Ra^T,
+// t = perp(Q d)), the corrected Jacobians are J_x = w C X0 with C = psi I + kappa e ebar^T
+// (ebar = (ex,ey,0), kappa = -psi/(phi+res) iff DCS active) and w^2 = rho' (Huber).  Hence
+//   J_x^T J_y = X0^T S Y0,  S = rho' C^T C = [[alpha I + c1 exy exy^T, c2 eth exy],[., alpha]],
+//   J_x^T r   = X0^T v,     v = (beta exy, alpha eth),
+//   alpha = rho' psi^2, c2 = -alpha/(phi+res), c1 = 2 c2 + alpha |e|^2/(phi+res)^2, beta = alpha + c2 |e|^2.
+// Rotating by Q (f = Q^T exy, Q^T t = perp(d) = n) every block is a combination of
+//   U = alpha I + c1 f f^T,  c = c2 eth f,  dv = alpha n + c1 (exy.t) f,  and a few scalars:
+//   H_aa = [[U, sigma c - dv],[., alpha(|t|^2+1) + c1 et^2 - 2 sigma ts2]]   g_a = (-beta f, beta et - sigma alpha eth)
+//   H_bb = [[U, sigma c],[., alpha]]                                         g_b = ( beta f, sigma alpha eth)
+//   H_ab = [[-U, -sigma c],[(dv - sigma c)^T, sigma ts2 - alpha]],  H_ba = H_ab^T,      ts2 = c2 eth et.
+// Only one reciprocal (DCS active) and one reciprocal square root (Huber active) per edge; psi and
+// sqrt(rho') themselves are never needed.  ~95 fp64 instructions instead of ~330 for the explicit J^T J.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {      // x normal, > 0
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {    // x normal, > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * y;
+  double e = fma(-x * y, y, 1.0);
+  y = fma(h, e, y);
+  h = 0.5 * y;
+  e = fma(-x * y, y, 1.0);
+  return fma(h, e, y);
+}
+__device__ __forceinline__ double fold_angle_fast(double d, double* sigma) {
+  const double inv2pi = 0.15915494309189533577;
+  const double twopi_hi = 6.283185307179586232;
+  const double twopi_lo = 2.4492935982947064e-16;
+  const double pi = 3.141592653589793116;
+  const double half_pi = 1.5707963267948966;
+  const double magic = 6755399441055744.0;              // 1.5 * 2^52: round-to-nearest-integer by addition
+  const double k = fma(d, inv2pi, magic) - magic;
+  double t = fma(-k, twopi_hi, d);
+  t = fma(-k, twopi_lo, t);
+  const bool hi = t > half_pi, lo = t < -half_pi;
+  *sigma = (hi || lo) ? -1.0 : 1.0;
+  return hi ? (pi - t) : (lo ? (-pi - t) : t);
+}
+
+struct EdgeTerms {
+  double U00, U01, U11;   // alpha I + c1 f f^T
+  double sc0, sc1;        // sigma * c
+  double e0, e1;          // dv - sigma c
+  double alpha;
+  double k22;             // alpha (|t|^2 + 1) + c1 et^2 - 2 sigma ts2
+  double o22;             // sigma ts2 - alpha
+  double bf0, bf1;        // beta f
+  double ga;              // beta et - sigma alpha eth        (gradient, theta of pose a)
+  double gb;              // sigma alpha eth                  (gradient, theta of pose b)
+  double cost;
+};
+
+__device__ __forceinline__ double edge_cost_terms(double xa, double ya, double tha, double ca, double sa,
+                                                  double xb, double yb, double thb,
+                                                  double tmx, double tmy, double thm, double cm, double sm,
+                                                  bool dcs, const Params& P,
+                                                  double& q00, double& q01, double& dxw, double& dyw, double& epx, double& epy,
+                                                  double& ex, double& ey, double& eth, double& sigma,
+                                                  double& psi2, double& inv_den, double& e2, double& rho1) {
+  q00 = fma(cm, ca, -sm * sa);
+  q01 = fma(cm, sa, sm * ca);
+  dxw = xb - xa; dyw = yb - ya;
+  epx = fma(q00, dxw, q01 * dyw);
+  epy = fma(q00, dyw, -q01 * dxw);
+  ex = epx - tmx; ey = epy - tmy;
+  eth = fold_angle_fast(thb - tha - thm, &sigma);
+  const double res = fma(ex, ex, ey * ey);
+  e2 = fma(eth, eth, res);
+  psi2 = 1.0; inv_den = 0.0;
+  if (dcs && res > P.phi) {                 // <=> psi_org < 1
+    inv_den = fast_rcp(P.phi + res);
+    psi2 = 2.0 * P.phi * inv_den;
+  }
+  const double s = psi2 * e2;
+  rho1 = 1.0;
+  double cost = 0.5 * s;
+  if (s > P.hub_b) {
+    const double rs = fast_rsqrt(s);
+    rho1 = P.hub_a * rs;                    // >= DBL_MIN for every finite s
+    cost = fma(P.hub_a, s * rs, -0.5 * P.hub_b);
+  }
+  return cost;
+}
+
+__device__ __forceinline__ void edge_terms(double xa, double ya, double tha, double ca, double sa,
+                                           double xb, double yb, double thb,
+                                           double tmx, double tmy, double thm, double cm, double sm,
+                                           bool dcs, const Params& P, EdgeTerms& T) {
+  double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
+  T.cost = edge_cost_terms(xa, ya, tha, ca, sa, xb, yb, thb, tmx, tmy, thm, cm, sm, dcs, P, q00, q01, dxw, dyw, epx, epy,
+                           ex, ey, eth, sigma, psi2, inv_den, e2, rho1);
+  const double alpha = rho1 * psi2;
+  const double c2 = -alpha * inv_den;                       // 0 unless DCS active
+  const double c1 = fma(alpha * e2, inv_den * inv_den, 2.0 * c2);
+  const double beta = fma(c2, e2, alpha);
+  const double f0 = fma(q00, ex, -q01 * ey);                // Q^T exy
+  const double f1 = fma(q01, ex, q00 * ey);
+  const double et = fma(ex, epy, -ey * epx);                // exy . t
+  const double tt = fma(epx, epx, epy * epy);               // |t|^2
+  const double cf0 = c1 * f0, cf1 = c1 * f1;
+  T.U00 = fma(cf0, f0, alpha);
+  T.U01 = cf0 * f1;
+  T.U11 = fma(cf1, f1, alpha);
+  const double k2 = c2 * eth * sigma;                       // sigma c2 eth
+  T.sc0 = k2 * f0; T.sc1 = k2 * f1;
+  const double k1 = c1 * et;
+  T.e0 = fma(k1, f0, fma(alpha, dyw, -T.sc0));              // dv - sigma c, dv = alpha n + k1 f, n = (dyw, -dxw)
+  T.e1 = fma(k1, f1, fma(-alpha, dxw, -T.sc1));
+  const double sts2 = k2 * et;                              // sigma ts2
+  T.alpha = alpha;
+  T.k22 = fma(k1, et, fma(alpha, tt + 1.0, -2.0 * sts2));
+  T.o22 = sts2 - alpha;
+  T.bf0 = beta * f0; T.bf1 = beta * f1;
+  const double sae = sigma * alpha * eth;
+  T.ga = fma(beta, et, -sae);
+  T.gb = sae;
+}
+
+// ------------------------------------------------------------------------------------------
 // cache-hinted accesses: matrix / half-edge streams are read once per pass (keep them out of
 // L1, first to leave L2); gathered vectors stay cached.
 // ------------------------------------------------------------------------------------------
+struct L2Policy { uint64_t stream, keep; };
+__device__ __forceinline__ L2Policy make_l2_policy() {
+  L2Policy p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+  return p;
+}
+__device__ __forceinline__ double ld_stream(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+// gathered operands (poses, the PCG direction vector): small, reused by every row that references them
+__device__ __forceinline__ double4 ld_keep4(const double4* p, uint64_t pol) {
+  double4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2+16], %3;" : "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ld_keep2(const double2* p, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+// plain (no policy) variant for the edge-order kernels
 __device__ __forceinline__ double ld_stream(const double* p) {
   double v;
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
-}
-__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_stream(double* p, double v) {
-  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -219,6 +379,85 @@ __device__ __forceinline__ void grid_reduce_max(double v, double* partials, unsi
     *out = t;
     *ticket = 0u;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic grid reduction for one-warp CTAs (the row-owner kernels): every CTA publishes K partial
+// sums (+ M maxima); the last CTA of each group of 64 folds that group, the last group folds the groups.
+// Fixed grouping and fold order -> bit-reproducible; no extra launch.
+// Workspace: part[(K+M) * n], gpart[(K+M) * ngroups], gticket[ngroups], ticket[1] (all zero-initialised).
+// ------------------------------------------------------------------------------------------------
+struct WarpRedWs { double* part; double* gpart; unsigned int* gticket; unsigned int* ticket; };
+constexpr int kRedGroup = 64;
+
+template <int K, int M>
+__device__ __forceinline__ void warp_grid_reduce(const double (&v)[K + M], const WarpRedWs& ws, double* out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int n = gridDim.x, cta = blockIdx.x;
+  const unsigned int ngroups = (n + kRedGroup - 1) / kRedGroup;
+  double x[K + M];
+#pragma unroll
+  for (int k = 0; k < K + M; ++k) {
+    x[k] = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, x[k], o);
+      x[k] = (k < K) ? x[k] + y : fmax(x[k], y);
+    }
+  }
+  unsigned int t = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K + M; ++k) ws.part[(size_t)k * n + cta] = x[k];
+    __threadfence();
+    t = atomicAdd(ws.gticket + cta / kRedGroup, 1u);
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  const unsigned int g = cta / kRedGroup;
+  const unsigned int gsize = min((unsigned int)kRedGroup, n - g * kRedGroup);
+  if (t != gsize - 1) return;
+  __threadfence();
+  // fold this group's partials: lane l takes entries l and l + 32, then a fixed shuffle tree
+#pragma unroll
+  for (int k = 0; k < K + M; ++k) {
+    const double* p = ws.part + (size_t)k * n + (size_t)g * kRedGroup;
+    double a = (lane < (int)gsize) ? __ldcg(p + lane) : 0.0;
+    const double b = (lane + 32 < (int)gsize) ? __ldcg(p + lane + 32) : 0.0;
+    a = (k < K) ? a + b : fmax(a, b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, a, o);
+      a = (k < K) ? a + y : fmax(a, y);
+    }
+    x[k] = a;
+  }
+  unsigned int t2 = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K + M; ++k) ws.gpart[(size_t)k * ngroups + g] = x[k];
+    ws.gticket[g] = 0u;                       // re-arm for the next launch
+    __threadfence();
+    t2 = atomicAdd(ws.ticket, 1u);
+  }
+  t2 = __shfl_sync(0xffffffffu, t2, 0);
+  if (t2 != ngroups - 1) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < K + M; ++k) {
+    const double* p = ws.gpart + (size_t)k * ngroups;
+    double a = 0.0;
+    for (unsigned int i = lane; i < ngroups; i += 32) {
+      const double y = __ldcg(p + i);
+      a = (k < K) ? a + y : fmax(a, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, a, o);
+      a = (k < K) ? a + y : fmax(a, y);
+    }
+    if (lane == 0) out[k] = a;
+  }
+  if (lane == 0) *ws.ticket = 0u;
 }
 
 }  // namespace dcs

@@ -26,10 +26,29 @@ struct RowLayout {           // jagged-diagonal layout of the owned rows
   int64_t ldn;               // leading dimension of per-row SoA arrays (>= gridDim * kRowsPerBlock)
   int64_t ldh;               // leading dimension of per-half-edge SoA arrays
   const int32_t* row_ptr;    // [nrows+1] sorted-CSR offsets (gives the degree)
-  const uint8_t* perm;       // [nblk*128] rank -> local row within the CTA
-  const int32_t* rp_off;     // [nblk]   offset of the CTA's rounds in round_ptr
+  const uint16_t* perm;      // [nwin*kWindow] rank -> local row within the window
+  const int32_t* rp_off;     // [nwin+1] offset of the window's rounds in round_ptr
   const int32_t* round_ptr;  // first slot of every round
+  int32_t nwin;              // windows of kWindow rows
+  int32_t ntasks;            // nwin * kSlicesPerWindow warp tasks
 };
+
+// Warp task mapping shared by the row-owner kernels: CTA = one warp = slice `sl` (ranks [32 sl, 32 sl + 32))
+// of degree-sorted window `win`.  Window-major order keeps concurrently running CTAs on neighbouring rows
+// (their gathered operands overlap in L2); within a window the longest slices start first.
+struct WarpTask { int lr; int rank; const int32_t* rp; bool valid; };
+__device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
+  WarpTask w;
+  const int task = blockIdx.x;
+  w.valid = task < L.ntasks;
+  const int win = w.valid ? task / kSlicesPerWindow : 0;
+  const int sl = w.valid ? task - win * kSlicesPerWindow : 0;
+  w.rank = sl * kSlice + (threadIdx.x & 31);
+  const int64_t slot0 = (int64_t)win * kWindow;
+  w.lr = (int)slot0 + L.perm[slot0 + w.rank];
+  w.rp = L.round_ptr + L.rp_off[win];
+  return w;
+}
 
 struct HalfEdges {           // per-half-edge SoA, in JDS slot order
   const uint32_t* other;     // other pose | flags
@@ -43,79 +62,127 @@ struct HalfEdges {           // per-half-edge SoA, in JDS slot order
 // ------------------------------------------------------------------------------------------------
 // K1 + K2
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowsPerBlock)
+struct HalfEdgeRec { double tmx, tmy, thm, cm, sm; };
+struct PoseRec { double x, y, th, c, s; };
+
+__device__ __forceinline__ HalfEdgeRec load_rec(const HalfEdges& H, int64_t idx, uint64_t pol) {
+  HalfEdgeRec r;
+  r.tmx = ld_stream(H.tmx + idx, pol); r.tmy = ld_stream(H.tmy + idx, pol); r.thm = ld_stream(H.thm + idx, pol);
+  r.cm = ld_stream(H.cm + idx, pol); r.sm = ld_stream(H.sm + idx, pol);
+  return r;
+}
+__device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, const double2* __restrict__ cs, uint32_t word,
+                                               uint64_t pol) {
+  const uint32_t j = word & kIdxMask;
+  const double4 p = ld_keep4(xyt + j, pol);
+  PoseRec r;
+  r.x = p.x; r.y = p.y; r.th = p.z; r.c = 1.0; r.s = 0.0;
+  if (word & kFlagSideB) { const double2 q = ld_keep2(cs + j, pol); r.c = q.x; r.s = q.y; }   // cos/sin only of the edge's first endpoint
+  return r;
+}
+
+// The assembled product is the reference's structure: the upper-triangular block matrix (one 3x3
+// off-diagonal block per edge, written by the half-edge whose row is the smaller endpoint: kFlagOwner),
+// the diagonal blocks and the gradient.  The mirrored (lower) copies the SpMV's full row storage wants
+// are filled by k_mirror as part of the linear-solver setup.
+__global__ void __launch_bounds__(kRowsPerBlock, 16)
 k_linearize(const double4* __restrict__ xyt, const double2* __restrict__ cs, RowLayout L, HalfEdges H, Params P,
             double* __restrict__ Hoff, double* __restrict__ Hdiag, double* __restrict__ grad,
-            double* partials, unsigned int* tickets, double* scal) {
-  const int t = threadIdx.x;
-  const int64_t slot0 = (int64_t)blockIdx.x * kRowsPerBlock;
-  const int lr = (int)slot0 + L.perm[slot0 + t];
+            WarpRedWs red, double* scal) {
+  const L2Policy pol = make_l2_policy();
+  const WarpTask wt = warp_task(L);
+  const int t = wt.rank;
+  const int lr = wt.lr;
+  const bool has_row = wt.valid && lr < L.nrows;
   int deg = 0;
   double ox = 0, oy = 0, oth = 0, oc = 1, os = 0;
-  if (lr < L.nrows) {
+  if (has_row) {
     deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
-    const double4 p = xyt[L.row_lo + lr];
-    const double2 q = cs[L.row_lo + lr];
+    const double4 p = ld_keep4(xyt + L.row_lo + lr, pol.keep);
+    const double2 q = ld_keep2(cs + L.row_lo + lr, pol.keep);
     ox = p.x; oy = p.y; oth = p.z; oc = q.x; os = q.y;
   }
-  const int32_t* rp = L.round_ptr + L.rp_off[blockIdx.x];
+  const int32_t* rp = wt.rp;
   double d00 = 0, d01 = 0, d02 = 0, d11 = 0, d12 = 0, d22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
-  for (int k = 0; k < deg; ++k) {
-    const int64_t idx = (int64_t)rp[k] + t;
-    const uint32_t word = ld_stream_u32(H.other + idx);
-    const double tmx = ld_stream(H.tmx + idx), tmy = ld_stream(H.tmy + idx), thm = ld_stream(H.thm + idx);
-    const double cm = ld_stream(H.cm + idx), sm = ld_stream(H.sm + idx);
-    const uint32_t j = word & kIdxMask;
+
+  auto process = [&](uint32_t word, const HalfEdgeRec& r, const PoseRec& pc, int64_t idx) {
     const bool side_b = (word & kFlagSideB) != 0;
-    const double4 pj = xyt[j];
-    double2 qj = make_double2(1.0, 0.0);
-    if (side_b) qj = cs[j];
     // edge frame: a = first endpoint, b = second
-    const double xa = side_b ? pj.x : ox, ya = side_b ? pj.y : oy, tha = side_b ? pj.z : oth;
-    const double ca = side_b ? qj.x : oc, sa = side_b ? qj.y : os;
-    const double xb = side_b ? ox : pj.x, yb = side_b ? oy : pj.y, thb = side_b ? oth : pj.z;
-    EdgeLin e;
-    edge_linearize<true>(xa, ya, tha, ca, sa, xb, yb, thb, tmx, tmy, thm, cm, sm, (word & kFlagDcs) != 0, P, e);
-    // R = Jacobian w.r.t. the row pose, O = w.r.t. the other pose
-    const double R00 = side_b ? e.b00 : e.a00, R01 = side_b ? e.b01 : e.a01, R02 = side_b ? 0.0 : e.a02;
-    const double R10 = side_b ? e.b10 : e.a10, R11 = side_b ? e.b11 : e.a11, R12 = side_b ? 0.0 : e.a12;
-    const double R20 = side_b ? e.b20 : e.a20, R21 = side_b ? e.b21 : e.a21, R22 = side_b ? e.b22 : e.a22;
-    const double O00 = side_b ? e.a00 : e.b00, O01 = side_b ? e.a01 : e.b01, O02 = side_b ? e.a02 : 0.0;
-    const double O10 = side_b ? e.a10 : e.b10, O11 = side_b ? e.a11 : e.b11, O12 = side_b ? e.a12 : 0.0;
-    const double O20 = side_b ? e.a20 : e.b20, O21 = side_b ? e.a21 : e.b21, O22 = side_b ? e.a22 : e.b22;
-    // diagonal block R^T R (symmetric) and gradient R^T r, accumulated in slot order
-    d00 += fma(R00, R00, fma(R10, R10, R20 * R20));
-    d01 += fma(R00, R01, fma(R10, R11, R20 * R21));
-    d02 += fma(R00, R02, fma(R10, R12, R20 * R22));
-    d11 += fma(R01, R01, fma(R11, R11, R21 * R21));
-    d12 += fma(R01, R02, fma(R11, R12, R21 * R22));
-    d22 += fma(R02, R02, fma(R12, R12, R22 * R22));
-    g0 += fma(R00, e.r0, fma(R10, e.r1, R20 * e.r2));
-    g1 += fma(R01, e.r0, fma(R11, e.r1, R21 * e.r2));
-    g2 += fma(R02, e.r0, fma(R12, e.r1, R22 * e.r2));
-    if (word & kFlagCost) cost += e.cost;
-    // off-diagonal block R^T O, zero when the other endpoint is constant
-    const double z = (word & kFlagOtherFixed) ? 0.0 : 1.0;
-    double* out = Hoff + idx;
-    st_stream(out + 0 * L.ldh, z * fma(R00, O00, fma(R10, O10, R20 * O20)));
-    st_stream(out + 1 * L.ldh, z * fma(R00, O01, fma(R10, O11, R20 * O21)));
-    st_stream(out + 2 * L.ldh, z * fma(R00, O02, fma(R10, O12, R20 * O22)));
-    st_stream(out + 3 * L.ldh, z * fma(R01, O00, fma(R11, O10, R21 * O20)));
-    st_stream(out + 4 * L.ldh, z * fma(R01, O01, fma(R11, O11, R21 * O21)));
-    st_stream(out + 5 * L.ldh, z * fma(R01, O02, fma(R11, O12, R21 * O22)));
-    st_stream(out + 6 * L.ldh, z * fma(R02, O00, fma(R12, O10, R22 * O20)));
-    st_stream(out + 7 * L.ldh, z * fma(R02, O01, fma(R12, O11, R22 * O21)));
-    st_stream(out + 8 * L.ldh, z * fma(R02, O02, fma(R12, O12, R22 * O22)));
+    const double xa = side_b ? pc.x : ox, ya = side_b ? pc.y : oy, tha = side_b ? pc.th : oth;
+    const double ca = side_b ? pc.c : oc, sa = side_b ? pc.s : os;
+    const double xb = side_b ? ox : pc.x, yb = side_b ? oy : pc.y, thb = side_b ? oth : pc.th;
+    EdgeTerms T;
+    edge_terms(xa, ya, tha, ca, sa, xb, yb, thb, r.tmx, r.tmy, r.thm, r.cm, r.sm, (word & kFlagDcs) != 0, P, T);
+    // diagonal block of the row pose and its gradient, accumulated in slot order
+    d00 += T.U00; d01 += T.U01; d11 += T.U11;
+    d02 += side_b ? T.sc0 : -T.e0;
+    d12 += side_b ? T.sc1 : -T.e1;
+    d22 += side_b ? T.alpha : T.k22;
+    g0 += side_b ? T.bf0 : -T.bf0;
+    g1 += side_b ? T.bf1 : -T.bf1;
+    g2 += side_b ? T.gb : T.ga;
+    if (word & kFlagCost) cost += T.cost;
+    if (word & kFlagOwner) {   // off-diagonal block (row pose x other pose)
+      double* out = Hoff + idx;
+      st_stream(out + 0 * L.ldh, -T.U00, pol.stream);
+      st_stream(out + 1 * L.ldh, -T.U01, pol.stream);
+      st_stream(out + 2 * L.ldh, side_b ? T.e0 : -T.sc0, pol.stream);
+      st_stream(out + 3 * L.ldh, -T.U01, pol.stream);
+      st_stream(out + 4 * L.ldh, -T.U11, pol.stream);
+      st_stream(out + 5 * L.ldh, side_b ? T.e1 : -T.sc1, pol.stream);
+      st_stream(out + 6 * L.ldh, side_b ? -T.sc0 : T.e0, pol.stream);
+      st_stream(out + 7 * L.ldh, side_b ? -T.sc1 : T.e1, pol.stream);
+      st_stream(out + 8 * L.ldh, T.o22, pol.stream);
+    }
+  };
+
+  // software pipeline, unrolled by two so buffers alternate instead of being copied: words run two
+  // rounds ahead, the measurement record and the gathered pose one round ahead
+  uint32_t w0 = 0, w1 = 0;
+  HalfEdgeRec recA, recB;
+  PoseRec poseA, poseB;
+  if (deg > 0) w0 = ld_stream_u32(H.other + rp[0] + t, pol.stream);
+  if (deg > 1) w1 = ld_stream_u32(H.other + rp[1] + t, pol.stream);
+  if (deg > 0) { recA = load_rec(H, (int64_t)rp[0] + t, pol.stream); poseA = gather_pose(xyt, cs, w0, pol.keep); }
+  for (int k = 0; k < deg; k += 2) {
+    uint32_t w2 = 0, w3 = 0;
+    if (k + 1 < deg) { recB = load_rec(H, (int64_t)rp[k + 1] + t, pol.stream); poseB = gather_pose(xyt, cs, w1, pol.keep); }
+    if (k + 2 < deg) w2 = ld_stream_u32(H.other + rp[k + 2] + t, pol.stream);
+    process(w0, recA, poseA, (int64_t)rp[k] + t);
+    if (k + 1 >= deg) break;
+    if (k + 2 < deg) { recA = load_rec(H, (int64_t)rp[k + 2] + t, pol.stream); poseA = gather_pose(xyt, cs, w2, pol.keep); }
+    if (k + 3 < deg) w3 = ld_stream_u32(H.other + rp[k + 3] + t, pol.stream);
+    process(w1, recB, poseB, (int64_t)rp[k + 1] + t);
+    w0 = w2; w1 = w3;
   }
-  if (lr < L.nrows) {
+  if (has_row) {
     Hdiag[0 * L.ldn + lr] = d00; Hdiag[1 * L.ldn + lr] = d01; Hdiag[2 * L.ldn + lr] = d02;
     Hdiag[3 * L.ldn + lr] = d11; Hdiag[4 * L.ldn + lr] = d12; Hdiag[5 * L.ldn + lr] = d22;
     grad[0 * L.ldn + lr] = g0; grad[1 * L.ldn + lr] = g1; grad[2 * L.ldn + lr] = g2;
   }
-  double sums[2] = {cost, fma(g0, g0, fma(g1, g1, g2 * g2))};
-  grid_reduce_sum<2, kRowsPerBlock>(sums, partials, tickets + 0, scal + S_COST);   // S_COST, S_GSQ
-  grid_reduce_max<kRowsPerBlock>(fmax(fabs(g0), fmax(fabs(g1), fabs(g2))), partials + 2 * (size_t)gridDim.x, tickets + 1,
-                                 scal + S_GMAX);
+  const double red_in[3] = {cost, fma(g0, g0, fma(g1, g1, g2 * g2)), fmax(fabs(g0), fmax(fabs(g1), fabs(g2)))};
+  warp_grid_reduce<2, 1>(red_in, red, scal + S_COST);   // S_COST, S_GSQ (sums), S_GMAX (max)
+}
+
+// Linear-solver setup: the SpMV walks full rows, so every non-owner slot receives the transpose of its
+// partner's block (mirror_src[slot] = partner slot, or -1 for owner slots / constant partners -> zero).
+__global__ void k_mirror(const int32_t* __restrict__ mirror_src, int32_t nh, int64_t ldh, double* Hoff) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int32_t s = mirror_src[i];
+  if (s == -1) return;                 // owner slot: already written by k_linearize
+  double v[9];
+  if (s >= 0) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = Hoff[(int64_t)c * ldh + s];
+  } else {                             // -2: the other endpoint is constant -> no block
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Hoff[(int64_t)(3 * r + c) * ldh + i] = v[3 * c + r];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -144,10 +211,10 @@ k_cost(const double4* __restrict__ xyt, const double2* __restrict__ cs, EdgeList
     const int32_t a = E.a[e], b = E.b[e];
     const double4 pa = xyt[a], pb = xyt[b];
     const double2 qa = cs[a];
-    EdgeLin L;
-    edge_linearize<false>(pa.x, pa.y, pa.z, qa.x, qa.y, pb.x, pb.y, pb.z, ld_stream(E.tmx + e), ld_stream(E.tmy + e),
-                          ld_stream(E.thm + e), ld_stream(E.cm + e), ld_stream(E.sm + e), E.dcs[e] != 0, P, L);
-    cost += L.cost;
+    double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
+    cost += edge_cost_terms(pa.x, pa.y, pa.z, qa.x, qa.y, pb.x, pb.y, pb.z, ld_stream(E.tmx + e), ld_stream(E.tmy + e),
+                            ld_stream(E.thm + e), ld_stream(E.cm + e), ld_stream(E.sm + e), E.dcs[e] != 0, P, q00, q01, dxw,
+                            dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1);
   }
   double s[1] = {cost};
   grid_reduce_sum<1, kEdgeThreads>(s, partials, ticket, out);
@@ -256,29 +323,49 @@ __global__ void k_precond(const double* __restrict__ Hdiag, const double* __rest
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowsPerBlock)
 k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__ other, const double* __restrict__ Hoff,
-       const double* __restrict__ D, double* __restrict__ q, double* partials, unsigned int* ticket, double* scal,
-       int dot_slot, int rotate_rz) {
-  const int t = threadIdx.x;
-  const int64_t slot0 = (int64_t)blockIdx.x * kRowsPerBlock;
-  const int lr = (int)slot0 + L.perm[slot0 + t];
+       const double* __restrict__ D, double* __restrict__ q, WarpRedWs red, double* scal, int dot_slot, int rotate_rz) {
+  const L2Policy pol = make_l2_policy();
+  const WarpTask wt = warp_task(L);
+  const int t = wt.rank;
+  const int lr = wt.lr;
   double y0 = 0, y1 = 0, y2 = 0, dot = 0;
-  if (lr < L.nrows) {
+  if (wt.valid && lr < L.nrows) {
     const int deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
-    const double4 p = p4[L.row_lo + lr];
+    const double4 p = ld_keep4(p4 + L.row_lo + lr, pol.keep);
     const double a00 = D[0 * L.ldn + lr], a01 = D[1 * L.ldn + lr], a02 = D[2 * L.ldn + lr];
     const double a11 = D[3 * L.ldn + lr], a12 = D[4 * L.ldn + lr], a22 = D[5 * L.ldn + lr];
     y0 = fma(a00, p.x, fma(a01, p.y, a02 * p.z));
     y1 = fma(a01, p.x, fma(a11, p.y, a12 * p.z));
     y2 = fma(a02, p.x, fma(a12, p.y, a22 * p.z));
-    const int32_t* rp = L.round_ptr + L.rp_off[blockIdx.x];
-    for (int k = 0; k < deg; ++k) {
+    const int32_t* rp = wt.rp;
+    constexpr int U = 4;     // rounds in flight per thread: 4 x (9 block words + column + gathered p) loads
+    int k = 0;
+    for (; k + U <= deg; k += U) {
+      int64_t idx[U]; uint32_t j[U]; double h[U][9]; double4 pj[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { idx[u] = (int64_t)rp[k + u] + t; j[u] = ld_stream_u32(other + idx[u], pol.stream) & kIdxMask; }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < 9; ++c) h[u][c] = ld_stream(Hoff + idx[u] + c * L.ldh, pol.stream);
+#pragma unroll
+      for (int u = 0; u < U; ++u) pj[u] = ld_keep4(p4 + j[u], pol.keep);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        y0 = fma(h[u][0], pj[u].x, fma(h[u][1], pj[u].y, fma(h[u][2], pj[u].z, y0)));
+        y1 = fma(h[u][3], pj[u].x, fma(h[u][4], pj[u].y, fma(h[u][5], pj[u].z, y1)));
+        y2 = fma(h[u][6], pj[u].x, fma(h[u][7], pj[u].y, fma(h[u][8], pj[u].z, y2)));
+      }
+    }
+    for (; k < deg; ++k) {
       const int64_t idx = (int64_t)rp[k] + t;
-      const uint32_t j = ld_stream_u32(other + idx) & kIdxMask;
+      const uint32_t j = ld_stream_u32(other + idx, pol.stream) & kIdxMask;
       const double* h = Hoff + idx;
-      const double h0 = ld_stream(h + 0 * L.ldh), h1 = ld_stream(h + 1 * L.ldh), h2 = ld_stream(h + 2 * L.ldh);
-      const double h3 = ld_stream(h + 3 * L.ldh), h4 = ld_stream(h + 4 * L.ldh), h5 = ld_stream(h + 5 * L.ldh);
-      const double h6 = ld_stream(h + 6 * L.ldh), h7 = ld_stream(h + 7 * L.ldh), h8 = ld_stream(h + 8 * L.ldh);
-      const double4 pj = p4[j];
+      const uint64_t ps = pol.stream;
+      const double h0 = ld_stream(h + 0 * L.ldh, ps), h1 = ld_stream(h + 1 * L.ldh, ps), h2 = ld_stream(h + 2 * L.ldh, ps);
+      const double h3 = ld_stream(h + 3 * L.ldh, ps), h4 = ld_stream(h + 4 * L.ldh, ps), h5 = ld_stream(h + 5 * L.ldh, ps);
+      const double h6 = ld_stream(h + 6 * L.ldh, ps), h7 = ld_stream(h + 7 * L.ldh, ps), h8 = ld_stream(h + 8 * L.ldh, ps);
+      const double4 pj = ld_keep4(p4 + j, pol.keep);
       y0 = fma(h0, pj.x, fma(h1, pj.y, fma(h2, pj.z, y0)));
       y1 = fma(h3, pj.x, fma(h4, pj.y, fma(h5, pj.z, y1)));
       y2 = fma(h6, pj.x, fma(h7, pj.y, fma(h8, pj.z, y2)));
@@ -286,9 +373,8 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
     q[0 * L.ldn + lr] = y0; q[1 * L.ldn + lr] = y1; q[2 * L.ldn + lr] = y2;
     dot = fma(p.x, y0, fma(p.y, y1, p.z * y2));
   }
-  double s[1] = {dot};
-  grid_reduce_sum<1, kRowsPerBlock>(s, partials, ticket, scal + dot_slot);
-  // grid_reduce_sum returns in every thread; only the finalising thread sees ticket == 0 reset.
+  const double red_in[1] = {dot};
+  warp_grid_reduce<1, 0>(red_in, red, scal + dot_slot);
   if (rotate_rz && threadIdx.x == 0 && blockIdx.x == 0) {
     // Safe: S_RZ / S_RZ_NEXT are not read by any thread of this kernel.
     scal[S_RZ] = scal[S_RZ_NEXT];

@@ -148,50 +148,55 @@ __global__ void k_row_ptr(const uint64_t* keys, int32_t nh, int32_t row_lo, int3
   row_ptr[r] = lo;
 }
 
-// ---- jagged-diagonal re-layout per CTA of kRowsPerBlock rows -------------------------------------
-// pass 1: rank of each row inside its CTA by decreasing degree (stable), max degree per CTA
-__global__ void k_jds_rank(const int32_t* row_ptr, int32_t nrows, uint8_t* rank_of, uint8_t* perm, int32_t* blk_rounds) {
-  __shared__ int32_t s_deg[kRowsPerBlock];
-  const int32_t r = blockIdx.x * kRowsPerBlock + threadIdx.x;
+// ---- jagged-diagonal re-layout per window of kWindow rows ----------------------------------------
+// Rows of a window are ranked by decreasing degree (stable); slot of (row, k-th entry) =
+// round_ptr[window][k] + rank(row).  A warp task = 32 consecutive ranks of one window: its lanes read 32
+// consecutive slots in every round (coalesced) and have near-equal degrees (97% lane efficiency at
+// kWindow = 1024 on the 1M-pose benchmark graph, 86% at 128).
+// pass 1: rank of each row inside its window, max degree per window
+__global__ void __launch_bounds__(kWindow)
+k_jds_rank(const int32_t* row_ptr, int32_t nrows, uint16_t* rank_of, uint16_t* perm, int32_t* win_rounds) {
+  __shared__ int32_t s_deg[kWindow];
+  const int32_t r = blockIdx.x * kWindow + threadIdx.x;
   const int32_t d = (r < nrows) ? row_ptr[r + 1] - row_ptr[r] : 0;
   s_deg[threadIdx.x] = d;
   __syncthreads();
   int rank = 0;
-  for (int u = 0; u < kRowsPerBlock; ++u) {
+  for (int u = 0; u < kWindow; ++u) {
     const int32_t du = s_deg[u];
     rank += (du > d) || (du == d && u < (int)threadIdx.x);
   }
-  rank_of[(int64_t)blockIdx.x * kRowsPerBlock + threadIdx.x] = (uint8_t)rank;
-  perm[(int64_t)blockIdx.x * kRowsPerBlock + rank] = (uint8_t)threadIdx.x;
-  if (rank == 0) blk_rounds[blockIdx.x] = d + 1;   // rounds + 1 entries in round_ptr
+  rank_of[(int64_t)blockIdx.x * kWindow + threadIdx.x] = (uint16_t)rank;
+  perm[(int64_t)blockIdx.x * kWindow + rank] = (uint16_t)threadIdx.x;
+  if (rank == 0) win_rounds[blockIdx.x] = d + 1;   // rounds + 1 entries in round_ptr
 }
-// pass 2: round_ptr[rp_off[b] + k] = first JDS slot of round k of CTA b
-__global__ void k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32_t* round_ptr) {
-  __shared__ int32_t s_deg[kRowsPerBlock];
-  const int32_t r0 = blockIdx.x * kRowsPerBlock;
+// pass 2: round_ptr[rp_off[w] + k] = first JDS slot of round k of window w
+__global__ void __launch_bounds__(kWindow)
+k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32_t* round_ptr) {
+  __shared__ int32_t s_deg[kWindow];
+  const int32_t r0 = blockIdx.x * kWindow;
   const int32_t r = r0 + threadIdx.x;
   s_deg[threadIdx.x] = (r < nrows) ? row_ptr[r + 1] - row_ptr[r] : 0;
   __syncthreads();
-  int32_t maxd = 0;
-  for (int u = 0; u < kRowsPerBlock; ++u) maxd = max(maxd, s_deg[u]);
   const int32_t base = row_ptr[min(r0, nrows)];
   const int32_t off = rp_off[blockIdx.x];
-  // round k starts after sum_{u<k} #{rows with deg > u} = sum_rows min(deg, k)
-  for (int32_t k = threadIdx.x; k <= maxd; k += kRowsPerBlock) {
+  const int32_t nround = rp_off[blockIdx.x + 1] - off;   // max degree + 1
+  // round k starts after sum_rows min(deg, k)
+  for (int32_t k = threadIdx.x; k < nround; k += kWindow) {
     int32_t s = 0;
-    for (int u = 0; u < kRowsPerBlock; ++u) s += min(s_deg[u], k);
+    for (int u = 0; u < kWindow; ++u) s += min(s_deg[u], k);
     round_ptr[off + k] = base + s;
   }
 }
 // pass 3: sorted CSR position -> JDS slot
 __global__ void k_jds_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, const int32_t* row_ptr,
-                           const uint8_t* rank_of, const int32_t* rp_off, const int32_t* round_ptr, int32_t* slot) {
+                           const uint16_t* rank_of, const int32_t* rp_off, const int32_t* round_ptr, int32_t* slot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const int32_t r = (int32_t)(keys[i] >> 32) - row_lo;
   const int32_t k = i - row_ptr[r];
-  const int32_t b = r / kRowsPerBlock;
-  slot[i] = round_ptr[rp_off[b] + k] + rank_of[r];
+  const int32_t w = r / kWindow;
+  slot[i] = round_ptr[rp_off[w] + k] + rank_of[r];
 }
 
 // ---- unique upper pattern (parity hook) ------------------------------------------------------------
