@@ -128,18 +128,24 @@ def main():
     import numpy as np
     import dcs_b200 as D
     dist = None
-    uid = None
     if world > 1:
         import torch
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def fresh_uid():
+        """A 128-byte NCCL id is good for ONE communicator: rank 0 draws it, everyone receives the same bytes."""
+        if not dist:
+            return None
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             buf = torch.frombuffer(bytearray(D.nccl_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
+
+    uid = fresh_uid()
 
     n_poses = POSES_PER_GPU * world
     g = D.Graph.synthetic(n_poses, LOOPS_PER_GPU * world - (world - 1), n_bogus=OUTLIERS_PER_GPU * world)
@@ -213,6 +219,8 @@ def main():
     lm = None
     if a.lm_iters > 0:
         s.close()
+        if dist:
+            opts["nccl_unique_id"] = fresh_uid()
         s = D.Solver(g, dcs_on=True, max_num_iterations=a.lm_iters, pcg_rel_tol=1e-8, pcg_max_iter=3000, **opts)
         t0 = time.perf_counter()
         xs, summ, trace = s.solve()

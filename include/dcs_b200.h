@@ -134,6 +134,11 @@ void dcs_options_default(dcs_options* o);
 const char* dcs_version(void);
 int dcs_device_count(void);
 
+/* Pose-range / edge-slice partition a handle with (rank, world) uses: contiguous, equal-sized pose ranges
+ * following the odometry chain (padded to the kernel's row window), equal edge slices for the cost-only
+ * kernel.  Pure host arithmetic (no CUDA): out = {row_lo, n_rows, rows_per_rank, edge_lo, edge_hi}. */
+int dcs_partition(int32_t n_poses, int32_t n_edges, int32_t rank, int32_t world, int32_t out[5]);
+
 /* 128-byte id for a multi-rank group; rank 0 calls it and ships the bytes to the peers. */
 int dcs_nccl_unique_id(void* out128);
 

@@ -261,3 +261,53 @@ def test_full_size_1m_poses_4m_edges_properties():
         h = 1e-6
         fd = (s.cost(g.pose_xyt + h * d) - s.cost(g.pose_xyt - h * d)) / (2 * h)
         assert abs(fd - (g1 * d).sum()) <= 1e-5 * abs(fd)
+
+
+def _write_g2o(path, g):
+    """g2o text from a flat graph (information values are placeholders: METHOD 0/1 never read them)."""
+    with open(path, "w") as f:
+        for i, p in enumerate(g.pose_xyt):
+            f.write("VERTEX_SE2 %d %.17g %.17g %.17g\n" % (i, p[0], p[1], p[2]))
+        for a, b, m in zip(g.edge_a, g.edge_b, g.meas_xyt):
+            f.write("EDGE_SE2 %d %d %.17g %.17g %.17g 1 0 0 1 0 1\n" % (a, b, m[0], m[1], m[2]))
+
+
+def test_drop_in_cli_do_build(tmp_path):
+    """`do_build.sh INTEL 50 1` (BASELINE config 1) end to end: same stdout lines, same four save/ files, final cost
+    equal to the oracle's.  INTEL.g2o is rebuilt from the committed golden arrays (the reference checkout is not on
+    the GPU box); DCS_SEED=1 reproduces the golden outlier loops (glibc rand())."""
+    import subprocess
+    from conftest import ROOT
+    pkg = os.path.join(ROOT, "toy-robust-backend-slam_b200")
+    g0, _ = load_case("INTEL_0_seed1")
+    g50, z = load_case("INTEL_50_seed1")
+    data = tmp_path / "data"; save = tmp_path / "save"
+    data.mkdir(); save.mkdir()
+    _write_g2o(str(data / "INTEL.g2o"), g0)
+    env = dict(os.environ, DCS_SEED="1", DCS_DATA_PATH=str(data), DCS_SAVE_PATH=str(save))
+    p = subprocess.run([os.path.join(pkg, "do_build.sh"), "INTEL", "50", "1"], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    out = p.stdout
+    order = ["Start Reading PoseGraph", "Adding Bogus edges as described in Vertigo paper", "writePoseGraph nodes: ",
+             "writePoseGraph Edges : ", "total nodes : 1228", "total nEdgesOdometry : 1227", "total nEdgesClosure : 256",
+             "total nEdgesBogus : 50", "iter      cost      cost_change", "Termination:   NO_CONVERGENCE"]
+    pos = [out.find(s) for s in order]
+    assert all(q >= 0 for q in pos) and pos == sorted(pos), pos
+    assert out.count("<--->") == 50
+    a, b = g50.edge_a[-50:], g50.edge_b[-50:]
+    assert "  %d<--->%d" % (a[0], b[0]) in out and "  %d<--->%d" % (a[-1], b[-1]) in out
+    for f in ("init_nodes.txt", "init_edges.txt", "opt_nodes.txt", "opt_edges.txt"):
+        assert (save / f).exists()
+    init = np.genfromtxt(save / "init_nodes.txt"); opt = np.genfromtxt(save / "opt_nodes.txt")
+    assert init.shape == opt.shape == (1228, 4)
+    assert np.allclose(init[:, 1:], g50.pose_xyt, rtol=1e-5, atol=1e-5)                    # 6 significant digits
+    assert np.allclose(opt[:, 1:], z["final_pose_dcs1"], rtol=2e-5, atol=2e-5)
+    edges = np.genfromtxt(save / "opt_edges.txt", dtype=int)
+    assert edges.shape == (1533, 3) and (edges[:, 2] == g50.kind).all()
+    import re
+    m = re.search(r"Final\s+([0-9.e+-]+)", out)
+    assert m and abs(float(m.group(1)) - float(z["final_cost_dcs1"])) <= 1e-6 * float(z["final_cost_dcs1"])
+    # METHOD 2/3/4 are refused, argc < 4 prints the usage
+    p2 = subprocess.run([os.path.join(pkg, "build", "main"), "INTEL", "0", "3"], capture_output=True, text=True, env=env,
+                        cwd=os.path.join(pkg, "build"))
+    assert p2.returncode == 2

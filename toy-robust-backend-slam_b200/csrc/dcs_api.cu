@@ -201,6 +201,10 @@ struct dcs_handle {
   DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
   DevBuf<double> partials, scal, stage3;   // stage3: N x 3 staging for host<->device AoS
   DevBuf<double> red_part, red_gpart;      // warp_grid_reduce workspace (row-owner kernels)
+  DevBuf<double> rank_scal;                // [world][4] per-rank (cost, gsq, gmax) after k_linearize
+  double* h_rank_scal = nullptr;
+  double lin_cost = 0, lin_gsq = 0, lin_gmax = 0;
+  bool lin_scal_pending = false;           // per-rank scalars not folded into h_scal yet
   DevBuf<unsigned int> red_tickets;        // [ngroups] group tickets + [1] global ticket
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
@@ -291,11 +295,6 @@ int allreduce_sum(dcs_handle* h, double* d, int count) {
   CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
   return DCS_OK;
 }
-int allreduce_max(dcs_handle* h, double* d, int count) {
-  if (h->world == 1) return DCS_OK;
-  CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclMax, h->comm, h->stream));
-  return DCS_OK;
-}
 // every rank owns rows [rank*rows_per_rank, ...) of a full-length array with `bytes_per_row`
 int allgather_rows(dcs_handle* h, void* full, size_t bytes_per_row) {
   if (h->world == 1) return DCS_OK;
@@ -307,7 +306,16 @@ int allgather_rows(dcs_handle* h, void* full, size_t bytes_per_row) {
 
 int read_scalars(dcs_handle* h) {
   CK(cudaMemcpyAsync(h->h_scal, h->scal.p, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->lin_scal_pending)
+    CK(cudaMemcpyAsync(h->h_rank_scal, h->rank_scal.p, (size_t)h->world * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->lin_scal_pending) {
+    double c = 0, g2 = 0, gm = 0;
+    for (int r = 0; r < h->world; ++r) { c += h->h_rank_scal[4 * r]; g2 += h->h_rank_scal[4 * r + 1]; gm = std::max(gm, h->h_rank_scal[4 * r + 2]); }
+    h->lin_cost = c; h->lin_gsq = g2; h->lin_gmax = gm;
+    h->lin_scal_pending = false;
+  }
+  if (h->world > 1) { h->h_scal[S_COST] = h->lin_cost; h->h_scal[S_GSQ] = h->lin_gsq; h->h_scal[S_GMAX] = h->lin_gmax; }
   return DCS_OK;
 }
 
@@ -330,8 +338,10 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 int linearize(dcs_handle* h, const double4* xyt, const double2* cs) {
   LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, cs, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
          h->grad.p, h->red(), h->scal.p);
-  CKS(allreduce_sum(h, h->scal.p + S_COST, 2));
-  CKS(allreduce_max(h, h->scal.p + S_GMAX, 1));
+  if (h->world > 1) {   // one collective: every rank's (cost, |g|^2, |g|_inf); folded on the host in rank order
+    CKN(nccl_api().AllGather(h->scal.p + S_COST, h->rank_scal.p, 4, ncclDouble, h->comm, h->stream));
+    h->lin_scal_pending = true;
+  }
   h->have_lin = true;
   h->mirrored = false;
   return DCS_OK;
@@ -464,6 +474,21 @@ int dcs_device_count(void) {
   return n;
 }
 
+int dcs_partition(int32_t n_poses, int32_t n_edges, int32_t rank, int32_t world, int32_t out[5]) {
+  if (!out || n_poses <= 0 || n_edges < 0 || world < 1 || rank < 0 || rank >= world) return DCS_ERR_ARG;
+  const int64_t tile = (int64_t)kWindow * world;
+  const int64_t npad = ((int64_t)n_poses + tile - 1) / tile * tile;
+  const int32_t rpr = (int32_t)(npad / world);
+  const int32_t row_lo = rank * rpr;
+  out[0] = row_lo;
+  out[1] = std::max(0, std::min(n_poses, row_lo + rpr) - row_lo);
+  out[2] = rpr;
+  const int64_t epr = ((int64_t)n_edges + world - 1) / world;
+  out[3] = (int32_t)std::min<int64_t>(n_edges, epr * rank);
+  out[4] = (int32_t)std::min<int64_t>(n_edges, epr * (rank + 1));
+  return DCS_OK;
+}
+
 int dcs_nccl_unique_id(void* out128) {
   if (!out128) return DCS_ERR_ARG;
   if (!nccl_api().load()) { g_err = "libnccl.so.2 not found"; return DCS_ERR_NCCL; }
@@ -479,6 +504,7 @@ void dcs_destroy(dcs_handle* h) {
   if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
   if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_rank_scal) cudaFreeHost(h->h_rank_scal);
   if (h->h_pin3) cudaFreeHost(h->h_pin3);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -526,18 +552,15 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
 
   // contiguous pose ranges, equal-sized (multiple of the CTA row tile) so in-place all-gathers work
   const int32_t N = h->N, E = h->E;
-  const int64_t tile = (int64_t)kWindow * h->world;
-  h->Npad = (int32_t)(((int64_t)N + tile - 1) / tile * tile);
-  h->rows_per_rank = h->Npad / h->world;
-  h->row_lo = h->rank * h->rows_per_rank;
-  h->nrows = std::max(0, std::min(N, h->row_lo + h->rows_per_rank) - h->row_lo);
+  int32_t part[5];
+  if (dcs_partition(N, E, h->rank, h->world, part) != DCS_OK) { g_err = "dcs_create: bad partition"; return DCS_ERR_ARG; }
+  h->row_lo = part[0]; h->nrows = part[1]; h->rows_per_rank = part[2];
+  h->Npad = h->rows_per_rank * h->world;
   h->nwin = std::max(1, h->rows_per_rank / kWindow);
   h->ntasks = h->nwin * kSlicesPerWindow;
   h->nblk = h->ntasks;                                // CTAs of the row-owner kernels (one warp task each)
   h->ldn = (int64_t)h->nwin * kWindow;
-  const int64_t epr = ((int64_t)E + h->world - 1) / h->world;
-  h->e_lo = (int32_t)std::min<int64_t>(E, epr * h->rank);
-  h->e_hi = (int32_t)std::min<int64_t>(E, epr * (h->rank + 1));
+  h->e_lo = part[3]; h->e_hi = part[4];
 
   // ---- upload the graph ---------------------------------------------------------------------
   DevBuf<double> d_meas;
@@ -639,6 +662,8 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1));
   CK(h->stage3.alloc_zero((size_t)N * 3));
   CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
+  CK(h->rank_scal.alloc_zero((size_t)h->world * 4));
+  CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
   CKS(upload_poses(h, g->pose_xyt, h->xyt.p, h->cs.p));
   CK(cudaStreamSynchronize(st));

@@ -57,7 +57,7 @@ class Summary(C.Structure):
 
 
 # every symbol include/dcs_b200.h declares (tests check the .so exports all of them)
-DECLARED_SYMBOLS = ["dcs_options_default", "dcs_version", "dcs_device_count", "dcs_nccl_unique_id", "dcs_create",
+DECLARED_SYMBOLS = ["dcs_options_default", "dcs_version", "dcs_device_count", "dcs_partition", "dcs_nccl_unique_id", "dcs_create",
                     "dcs_destroy", "dcs_evaluate", "dcs_linearize", "dcs_linearize_resident", "dcs_cost",
                     "dcs_get_pattern", "dcs_get_hessian", "dcs_pcg_solve", "dcs_solve", "dcs_last_error",
                     "dcs_launch_count"]
@@ -141,6 +141,16 @@ def device_count():
 
 def launch_count(reset=False):
     return int(load_library().dcs_launch_count(1 if reset else 0))
+
+
+def partition(n_poses, n_edges, rank, world):
+    """(row_lo, n_rows, rows_per_rank, edge_lo, edge_hi) of a rank; pure host arithmetic."""
+    out = (C.c_int32 * 5)()
+    lib = load_library()
+    rc = lib.dcs_partition(n_poses, n_edges, rank, world, out)
+    if rc:
+        raise DcsError(rc, "dcs_partition", "bad argument")
+    return tuple(out)
 
 
 def nccl_unique_id():
