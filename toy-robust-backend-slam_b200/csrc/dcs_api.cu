@@ -81,7 +81,7 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 // per-edge constants: (tmx,tmy) = Rm^T (dx,dy), cos/sin of the measured rotation, DCS flag
 __global__ void k_edge_prep(const double* __restrict__ meas, const uint8_t* __restrict__ kind, int32_t E, int dcs_on,
-                            double* tmx, double* tmy, double* thm, double* cm, double* sm, uint8_t* dcs_flag) {
+                            double* tmx, double* tmy, double* thm, uint8_t* dcs_flag) {
   const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const double dx = meas[3 * (int64_t)e], dy = meas[3 * (int64_t)e + 1], th = meas[3 * (int64_t)e + 2];
@@ -89,7 +89,7 @@ __global__ void k_edge_prep(const double* __restrict__ meas, const uint8_t* __re
   sincos(th, &s, &c);
   tmx[e] = fma(c, dx, s * dy);
   tmy[e] = fma(c, dy, -s * dx);
-  thm[e] = th; cm[e] = c; sm[e] = s;
+  thm[e] = th;
   dcs_flag[e] = (dcs_on && kind[e] != DCS_EDGE_ODOMETRY) ? 1 : 0;
 }
 
@@ -97,16 +97,15 @@ __global__ void k_edge_prep(const double* __restrict__ meas, const uint8_t* __re
 __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const int32_t* __restrict__ slot,
                                  int32_t nh, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                  const int32_t* __restrict__ deg_all, int32_t fixed, const double* __restrict__ tmx,
-                                 const double* __restrict__ tmy, const double* __restrict__ thm, const double* __restrict__ cm,
-                                 const double* __restrict__ sm, const uint8_t* __restrict__ dcs_flag, int32_t row_lo, int32_t row_hi,
-                                 uint32_t* h_other, double* h_tmx, double* h_tmy, double* h_thm, double* h_cm, double* h_sm,
-                                 int32_t* edge_slot) {
+                                 const double* __restrict__ tmy, const double* __restrict__ thm,
+                                 const uint8_t* __restrict__ dcs_flag, int32_t row_lo, int32_t row_hi,
+                                 uint32_t* h_other, double* h_tmx, double* h_tmy, double* h_thm, int32_t* edge_slot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const uint32_t v = vals[i];
   const int32_t e = (int32_t)(v >> 1);
   const bool side_b = (v & 1u) != 0;
-  const int32_t other = (int32_t)(keys[i] & 0xFFFFFFFFu);
+  const int32_t other = (int32_t)(keys[i] & kIdxMask);
   const int32_t row = (int32_t)(keys[i] >> 32);
   const int32_t a = ea[e];
   uint32_t word = (uint32_t)other;
@@ -120,7 +119,7 @@ __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32
   if ((!side_b && a_has_row) || (side_b && !a_has_row)) word |= kFlagCost;
   const int32_t s = slot[i];
   h_other[s] = word;
-  h_tmx[s] = tmx[e]; h_tmy[s] = tmy[e]; h_thm[s] = thm[e]; h_cm[s] = cm[e]; h_sm[s] = sm[e];
+  h_tmx[s] = tmx[e]; h_tmy[s] = tmy[e]; h_thm[s] = thm[e];
   edge_slot[2 * (int64_t)e + (side_b ? 1 : 0)] = s;
   (void)deg_all; (void)eb;
 }
@@ -183,7 +182,7 @@ struct dcs_handle {
   int64_t ldn = 0, ldh = 0;
   // graph (device)
   DevBuf<int32_t> ea, eb, deg_all;
-  DevBuf<double> e_tmx, e_tmy, e_thm, e_cm, e_sm;
+  DevBuf<double> e_tmx, e_tmy, e_thm;
   DevBuf<uint8_t> e_dcs, is_free;
   // pattern
   DevBuf<uint64_t> keys;        // sorted (row<<32|col)
@@ -194,10 +193,9 @@ struct dcs_handle {
   int32_t n_upper = 0;
   // half-edges (JDS order)
   DevBuf<uint32_t> h_other;
-  DevBuf<double> h_tmx, h_tmy, h_thm, h_cm, h_sm;
+  DevBuf<double> h_tmx, h_tmy, h_thm;
   // state
   DevBuf<double4> xyt, cand_xyt, p4;
-  DevBuf<double2> cs, cand_cs;
   DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
   DevBuf<double> partials, scal, stage3;   // stage3: N x 3 staging for host<->device AoS
   DevBuf<double> red_part, red_gpart;      // warp_grid_reduce workspace (row-owner kernels)
@@ -225,12 +223,12 @@ struct dcs_handle {
   }
   HalfEdges halfedges() const {
     HalfEdges H;
-    H.other = h_other.p; H.tmx = h_tmx.p; H.tmy = h_tmy.p; H.thm = h_thm.p; H.cm = h_cm.p; H.sm = h_sm.p;
+    H.other = h_other.p; H.tmx = h_tmx.p; H.tmy = h_tmy.p; H.thm = h_thm.p;
     return H;
   }
   EdgeList edgelist() const {
     EdgeList L;
-    L.n = E; L.a = ea.p; L.b = eb.p; L.tmx = e_tmx.p; L.tmy = e_tmy.p; L.thm = e_thm.p; L.cm = e_cm.p; L.sm = e_sm.p; L.dcs = e_dcs.p;
+    L.n = E; L.a = ea.p; L.b = eb.p; L.tmx = e_tmx.p; L.tmy = e_tmy.p; L.thm = e_thm.p; L.dcs = e_dcs.p;
     return L;
   }
   int vec_grid() const { return std::max(1, cdiv(nrows, kVecThreads)); }
@@ -320,10 +318,10 @@ int read_scalars(dcs_handle* h) {
 }
 
 // host N x 3 poses -> device packed poses (+ cos/sin)
-int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt, double2* cs) {
+int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt) {
   std::memcpy(h->h_pin3, pose_xyt, (size_t)h->N * 3 * sizeof(double));
   CK(cudaMemcpyAsync(h->stage3.p, h->h_pin3, (size_t)h->N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(k_pack_poses, cdiv(h->N, 256), 256, h->stream, h->stage3.p, h->N, xyt, cs);
+  LAUNCH(k_pack_poses, cdiv(h->N, 256), 256, h->stream, h->stage3.p, h->N, xyt);
   return DCS_OK;
 }
 int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
@@ -335,8 +333,8 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 }
 
 // K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
-int linearize(dcs_handle* h, const double4* xyt, const double2* cs) {
-  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, cs, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
+int linearize(dcs_handle* h, const double4* xyt) {
+  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
          h->grad.p, h->red(), h->scal.p);
   if (h->world > 1) {   // one collective: every rank's (cost, |g|^2, |g|_inf); folded on the host in rank order
     CKN(nccl_api().AllGather(h->scal.p + S_COST, h->rank_scal.p, 4, ncclDouble, h->comm, h->stream));
@@ -355,10 +353,10 @@ int ensure_mirror(dcs_handle* h) {
   return DCS_OK;
 }
 
-int cost_only(dcs_handle* h, const double4* xyt, const double2* cs, int slot) {
+int cost_only(dcs_handle* h, const double4* xyt, int slot) {
   const int ne = h->e_hi - h->e_lo;
   const int grid = std::max(1, std::min(cdiv(ne, kEdgeThreads), 148 * 8));
-  LAUNCH(k_cost, grid, kEdgeThreads, h->stream, xyt, cs, h->edgelist(), h->e_lo, h->e_hi, h->P, h->partials.p, h->tickets.p + 2,
+  LAUNCH(k_cost, grid, kEdgeThreads, h->stream, xyt, h->edgelist(), h->e_lo, h->e_hi, h->P, h->partials.p, h->tickets.p + 2,
          h->scal.p + slot);
   CKS(allreduce_sum(h, h->scal.p + slot, 1));
   return DCS_OK;
@@ -574,10 +572,10 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     CK(cudaMemcpyAsync(d_kind.p, g->kind, (size_t)E, cudaMemcpyHostToDevice, st));
   }
   const size_t EE = (size_t)std::max(E, 1);
-  CK(h->e_tmx.alloc(EE)); CK(h->e_tmy.alloc(EE)); CK(h->e_thm.alloc(EE)); CK(h->e_cm.alloc(EE)); CK(h->e_sm.alloc(EE));
+  CK(h->e_tmx.alloc(EE)); CK(h->e_tmy.alloc(EE)); CK(h->e_thm.alloc(EE));
   CK(h->e_dcs.alloc(EE));
   if (E > 0) LAUNCH(k_edge_prep, cdiv(E, 256), 256, st, d_meas.p, d_kind.p, E, o->dcs_on, h->e_tmx.p, h->e_tmy.p, h->e_thm.p,
-                    h->e_cm.p, h->e_sm.p, h->e_dcs.p);
+                    h->e_dcs.p);
 
   // ---- K0: half-edges, sort, CSR, jagged-diagonal re-layout ---------------------------------------
   CK(h->deg_all.alloc_zero((size_t)h->Npad));
@@ -622,15 +620,14 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
 
   const size_t HH = (size_t)h->ldh;
   CK(h->h_other.alloc_zero(HH)); CK(h->h_tmx.alloc_zero(HH)); CK(h->h_tmy.alloc_zero(HH)); CK(h->h_thm.alloc_zero(HH));
-  CK(h->h_cm.alloc_zero(HH)); CK(h->h_sm.alloc_zero(HH));
   CK(h->mirror_src.alloc((size_t)std::max(nh, 1)));
   if (nh > 0) {
     DevBuf<int32_t> edge_slot;
     CK(edge_slot.alloc((size_t)2 * EE));
     CK(cudaMemsetAsync(edge_slot.p, 0xFF, (size_t)2 * EE * 4, st));
     LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
-           h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_cm.p, h->e_sm.p, h->e_dcs.p, h->row_lo, row_hi, h->h_other.p,
-           h->h_tmx.p, h->h_tmy.p, h->h_thm.p, h->h_cm.p, h->h_sm.p, edge_slot.p);
+           h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->h_other.p,
+           h->h_tmx.p, h->h_tmy.p, h->h_thm.p, edge_slot.p);
     LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, h->mirror_src.p);
     CK(cudaStreamSynchronize(st));
   }
@@ -648,7 +645,6 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   // ---- state --------------------------------------------------------------------------------------
   const size_t NP = (size_t)h->Npad, LN = (size_t)h->ldn;
   CK(h->xyt.alloc_zero(NP)); CK(h->cand_xyt.alloc_zero(NP)); CK(h->p4.alloc_zero(NP));
-  CK(h->cs.alloc_zero(NP)); CK(h->cand_cs.alloc_zero(NP));
   CK(h->Hoff.alloc_zero(9 * HH)); CK(h->Hdiag.alloc_zero(6 * LN)); CK(h->grad.alloc_zero(3 * LN));
   CK(h->scale.alloc_zero(3 * LN)); CK(h->lmdiag.alloc_zero(3 * LN)); CK(h->Adiag.alloc_zero(6 * LN)); CK(h->Minv.alloc_zero(6 * LN));
   CK(h->w.alloc_zero(3 * LN)); CK(h->r.alloc_zero(3 * LN)); CK(h->q.alloc_zero(3 * LN)); CK(h->z.alloc_zero(3 * LN));
@@ -665,7 +661,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->rank_scal.alloc_zero((size_t)h->world * 4));
   CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
-  CKS(upload_poses(h, g->pose_xyt, h->xyt.p, h->cs.p));
+  CKS(upload_poses(h, g->pose_xyt, h->xyt.p));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   guard.h = nullptr;
@@ -677,8 +673,8 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
                  double* rho1, double* gradient) {
   if (!h) return DCS_ERR_ARG;
   CK(cudaSetDevice(h->dev));
-  if (pose_xyt) CKS(upload_poses(h, pose_xyt, h->xyt.p, h->cs.p));
-  CKS(linearize(h, h->xyt.p, h->cs.p));
+  if (pose_xyt) CKS(upload_poses(h, pose_xyt, h->xyt.p));
+  CKS(linearize(h, h->xyt.p));
   CKS(read_scalars(h));
   if (cost) *cost = h->h_scal[S_COST];
   const int32_t E = h->E;
@@ -688,7 +684,7 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
     if (jacobians) CK(dj.alloc((size_t)E * 18));
     if (psi) CK(dp.alloc((size_t)E));
     if (rho1) CK(dq.alloc((size_t)E));
-    LAUNCH(k_edge_eval, cdiv(E, kEdgeThreads), kEdgeThreads, h->stream, h->xyt.p, h->cs.p, h->edgelist(), h->P, dr.p, dj.p, dp.p, dq.p);
+    LAUNCH(k_edge_eval, cdiv(E, kEdgeThreads), kEdgeThreads, h->stream, h->xyt.p, h->edgelist(), h->P, dr.p, dj.p, dp.p, dq.p);
     if (residuals) CK(cudaMemcpyAsync(residuals, dr.p, (size_t)E * 24, cudaMemcpyDeviceToHost, h->stream));
     if (jacobians) CK(cudaMemcpyAsync(jacobians, dj.p, (size_t)E * 144, cudaMemcpyDeviceToHost, h->stream));
     if (psi) CK(cudaMemcpyAsync(psi, dp.p, (size_t)E * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -710,8 +706,8 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
 int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* gradient) {
   if (!h || !pose_xyt) return DCS_ERR_ARG;
   CK(cudaSetDevice(h->dev));
-  CKS(upload_poses(h, pose_xyt, h->xyt.p, h->cs.p));
-  CKS(linearize(h, h->xyt.p, h->cs.p));
+  CKS(upload_poses(h, pose_xyt, h->xyt.p));
+  CKS(linearize(h, h->xyt.p));
   if (gradient && h->nrows > 0) {
     LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->nrows, h->ldn, h->stage3.p);
     CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)h->nrows * 24, cudaMemcpyDeviceToHost, h->stream));
@@ -729,7 +725,7 @@ int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total) {
   if (!h || repeats <= 0) return DCS_ERR_ARG;
   CK(cudaSetDevice(h->dev));
   CK(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < repeats; ++i) CKS(linearize(h, h->xyt.p, h->cs.p));
+  for (int i = 0; i < repeats; ++i) CKS(linearize(h, h->xyt.p));
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
   float ms = 0;
@@ -742,9 +738,9 @@ int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total) {
 int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost) {
   if (!h || !cost) return DCS_ERR_ARG;
   CK(cudaSetDevice(h->dev));
-  const double4* x = h->xyt.p; const double2* c = h->cs.p;
-  if (pose_xyt) { CKS(upload_poses(h, pose_xyt, h->cand_xyt.p, h->cand_cs.p)); x = h->cand_xyt.p; c = h->cand_cs.p; }
-  CKS(cost_only(h, x, c, S_CAND_COST));
+  const double4* x = h->xyt.p;
+  if (pose_xyt) { CKS(upload_poses(h, pose_xyt, h->cand_xyt.p)); x = h->cand_xyt.p; }
+  CKS(cost_only(h, x, S_CAND_COST));
   CKS(read_scalars(h));
   *cost = h->h_scal[S_CAND_COST];
   return DCS_OK;
@@ -774,7 +770,7 @@ int dcs_get_pattern(dcs_handle* h, int32_t* n_block_rows, int32_t* nnzb, int32_t
     row_ptr[r] = pos;
     if (is_free[r]) col_idx[pos++] = r;
     while (i < keys.size() && (int32_t)(keys[i] >> 32) == r) {
-      if (flag[i]) col_idx[pos++] = (int32_t)(keys[i] & 0xFFFFFFFFu);
+      if (flag[i]) col_idx[pos++] = (int32_t)(keys[i] & kIdxMask);
       ++i;
     }
   }
@@ -866,9 +862,9 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
   cudaStream_t st = h->stream;
   float ms = 0;
 
-  auto timed_linearize = [&](const double4* x, const double2* c) -> int {
+  auto timed_linearize = [&](const double4* x) -> int {
     CK(cudaEventRecord(h->ev0, st));
-    CKS(linearize(h, x, c));
+    CKS(linearize(h, x));
     CK(cudaEventRecord(h->ev1, st));
     CKS(read_scalars(h));
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -876,10 +872,10 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     return DCS_OK;
   };
 
-  CKS(upload_poses(h, pose_xyt_inout, h->xyt.p, h->cs.p));
+  CKS(upload_poses(h, pose_xyt_inout, h->xyt.p));
   LAUNCH(k_xnorm, h->vec_grid(), kVecThreads, st, h->xyt.p, h->is_free.p, h->row_lo, h->nrows, h->partials.p, h->tickets.p + 5, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_XSQ, 1));
-  CKS(timed_linearize(h->xyt.p, h->cs.p));
+  CKS(timed_linearize(h->xyt.p));
   double x_cost = h->h_scal[S_COST];
   double x_norm = std::sqrt(h->h_scal[S_XSQ]);
   if (!std::isfinite(x_cost)) {
@@ -953,12 +949,11 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
     // candidate = x - w
     LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->cand_xyt.p,
-           h->cand_cs.p, h->partials.p, h->tickets.p + 5, h->scal.p);
+           h->partials.p, h->tickets.p + 5, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_STEP_SQ, 2));
     CKS(allgather_rows(h, h->cand_xyt.p, sizeof(double4)));
-    CKS(allgather_rows(h, h->cand_cs.p, sizeof(double2)));
     CK(cudaEventRecord(h->ev0, st));
-    CKS(cost_only(h, h->cand_xyt.p, h->cand_cs.p, S_CAND_COST));
+    CKS(cost_only(h, h->cand_xyt.p, S_CAND_COST));
     CK(cudaEventRecord(h->ev1, st));
     CKS(read_scalars(h));
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1000,9 +995,8 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
                                                                           : (x_cost - cand) / model_cost_change;
     if (it.relative_decrease > o.min_relative_decrease) {
       std::swap(h->xyt.p, h->cand_xyt.p);
-      std::swap(h->cs.p, h->cand_cs.p);
       x_norm = std::sqrt(h->h_scal[S_XSQ]);
-      CKS(timed_linearize(h->xyt.p, h->cs.p));
+      CKS(timed_linearize(h->xyt.p));
       x_cost = h->h_scal[S_COST];
       it.step_is_successful = 1;
       it.cost = x_cost;

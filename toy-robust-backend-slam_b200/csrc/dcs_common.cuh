@@ -15,6 +15,7 @@ constexpr int kRowsPerBlock = 32;        // threads per CTA in the row-owner ker
 constexpr int kWindow = 1024;            // rows per jagged-diagonal window (sorted by degree inside it)
 constexpr int kSlice = 32;               // rows per warp task
 constexpr int kSlicesPerWindow = kWindow / kSlice;
+constexpr uint32_t kKeyNonOwner = 1u << 31;  // sort-key bit (col word): non-owner half-edges follow a row's owner ones
 constexpr uint32_t kIdxMask = 0x07FFFFFFu;  // low 27 bits of a half-edge word: other pose (<= 134M poses)
 constexpr uint32_t kFlagSideB = 1u << 31;   // row pose is the edge's second endpoint (Edge::b)
 constexpr uint32_t kFlagDcs = 1u << 30;     // DCS functor applies (loop/bogus edge and METHOD 1)
@@ -41,7 +42,7 @@ struct Params {
 //   DCS: psi = min(1, sqrt(2 phi / (phi + ex^2 + ey^2))), r = psi e,
 //        J = psi J_e + e (grad psi)^T, grad psi = -psi/(phi+res) (ex grad ex + ey grad ey) iff psi<1
 //   Huber: s = |r|^2 > delta^2 -> rho' = delta / sqrt(s); r, J scaled by sqrt(rho'); cost = rho/2.
-// Measurement is pre-rotated once at upload: (tmx,tmy) = Rm^T (dx,dy).
+// Measurement is pre-rotated once at upload: (tmx,tmy) = Rm^T (dx,dy); cos/sin(tha+thm) come from one sincos.
 // ------------------------------------------------------------------------------------------
 struct EdgeLin {
   double r0, r1, r2;                                // corrected residual
@@ -66,12 +67,12 @@ __device__ __forceinline__ double fold_angle(double d, double* sigma) {
 }
 
 template <bool kNeedJac>
-__device__ __forceinline__ void edge_linearize(double xa, double ya, double tha, double ca, double sa,
+__device__ __forceinline__ void edge_linearize(double xa, double ya, double tha,
                                                double xb, double yb, double thb,
-                                               double tmx, double tmy, double thm, double cm, double sm,
+                                               double tmx, double tmy, double thm,
                                                bool dcs, const Params& P, EdgeLin& L) {
-  const double q00 = fma(cm, ca, -sm * sa);   // cos(tha + thm)
-  const double q01 = fma(cm, sa, sm * ca);    // sin(tha + thm)
+  double q00, q01;                             // cos / sin (tha + thm): Q = Rm^T Ra^T = R(-(tha + thm))
+  sincos(tha + thm, &q01, &q00);
   const double dxw = xb - xa, dyw = yb - ya;
   const double epx = fma(q00, dxw, q01 * dyw);    // Q d
   const double epy = fma(q00, dyw, -q01 * dxw);
@@ -180,15 +181,15 @@ struct EdgeTerms {
   double cost;
 };
 
-__device__ __forceinline__ double edge_cost_terms(double xa, double ya, double tha, double ca, double sa,
+__device__ __forceinline__ double edge_cost_terms(double xa, double ya, double tha,
                                                   double xb, double yb, double thb,
-                                                  double tmx, double tmy, double thm, double cm, double sm,
+                                                  double tmx, double tmy, double thm,
                                                   bool dcs, const Params& P,
                                                   double& q00, double& q01, double& dxw, double& dyw, double& epx, double& epy,
                                                   double& ex, double& ey, double& eth, double& sigma,
                                                   double& psi2, double& inv_den, double& e2, double& rho1) {
-  q00 = fma(cm, ca, -sm * sa);
-  q01 = fma(cm, sa, sm * ca);
+  sincos(tha + thm, &q01, &q00);            // one sincos per half-edge instead of streaming cos/sin of the
+                                            // measurement and gathering cos/sin of the pose (28 B less traffic)
   dxw = xb - xa; dyw = yb - ya;
   epx = fma(q00, dxw, q01 * dyw);
   epy = fma(q00, dyw, -q01 * dxw);
@@ -212,12 +213,12 @@ __device__ __forceinline__ double edge_cost_terms(double xa, double ya, double t
   return cost;
 }
 
-__device__ __forceinline__ void edge_terms(double xa, double ya, double tha, double ca, double sa,
+__device__ __forceinline__ void edge_terms(double xa, double ya, double tha,
                                            double xb, double yb, double thb,
-                                           double tmx, double tmy, double thm, double cm, double sm,
+                                           double tmx, double tmy, double thm,
                                            bool dcs, const Params& P, EdgeTerms& T) {
   double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
-  T.cost = edge_cost_terms(xa, ya, tha, ca, sa, xb, yb, thb, tmx, tmy, thm, cm, sm, dcs, P, q00, q01, dxw, dyw, epx, epy,
+  T.cost = edge_cost_terms(xa, ya, tha, xb, yb, thb, tmx, tmy, thm, dcs, P, q00, q01, dxw, dyw, epx, epy,
                            ex, ey, eth, sigma, psi2, inv_den, e2, rho1);
   const double alpha = rho1 * psi2;
   const double c2 = -alpha * inv_den;                       // 0 unless DCS active

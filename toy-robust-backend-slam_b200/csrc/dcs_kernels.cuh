@@ -50,34 +50,28 @@ __device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
   return w;
 }
 
-struct HalfEdges {           // per-half-edge SoA, in JDS slot order
+struct HalfEdges {           // per-half-edge SoA, in JDS slot order: 28 B per half-edge
   const uint32_t* other;     // other pose | flags
   const double* tmx;         // Rm^T (dx,dy)
   const double* tmy;
   const double* thm;
-  const double* cm;
-  const double* sm;
 };
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K2
 // ------------------------------------------------------------------------------------------------
-struct HalfEdgeRec { double tmx, tmy, thm, cm, sm; };
-struct PoseRec { double x, y, th, c, s; };
+struct HalfEdgeRec { double tmx, tmy, thm; };
+struct PoseRec { double x, y, th; };
 
 __device__ __forceinline__ HalfEdgeRec load_rec(const HalfEdges& H, int64_t idx, uint64_t pol) {
   HalfEdgeRec r;
   r.tmx = ld_stream(H.tmx + idx, pol); r.tmy = ld_stream(H.tmy + idx, pol); r.thm = ld_stream(H.thm + idx, pol);
-  r.cm = ld_stream(H.cm + idx, pol); r.sm = ld_stream(H.sm + idx, pol);
   return r;
 }
-__device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, const double2* __restrict__ cs, uint32_t word,
-                                               uint64_t pol) {
-  const uint32_t j = word & kIdxMask;
-  const double4 p = ld_keep4(xyt + j, pol);
+__device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, uint32_t word, uint64_t pol) {
+  const double4 p = ld_keep4(xyt + (word & kIdxMask), pol);     // one 32-byte sector per gathered pose
   PoseRec r;
-  r.x = p.x; r.y = p.y; r.th = p.z; r.c = 1.0; r.s = 0.0;
-  if (word & kFlagSideB) { const double2 q = ld_keep2(cs + j, pol); r.c = q.x; r.s = q.y; }   // cos/sin only of the edge's first endpoint
+  r.x = p.x; r.y = p.y; r.th = p.z;
   return r;
 }
 
@@ -86,7 +80,7 @@ __device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, 
 // the diagonal blocks and the gradient.  The mirrored (lower) copies the SpMV's full row storage wants
 // are filled by k_mirror as part of the linear-solver setup.
 __global__ void __launch_bounds__(kRowsPerBlock, 16)
-k_linearize(const double4* __restrict__ xyt, const double2* __restrict__ cs, RowLayout L, HalfEdges H, Params P,
+k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
             double* __restrict__ Hoff, double* __restrict__ Hdiag, double* __restrict__ grad,
             WarpRedWs red, double* scal) {
   const L2Policy pol = make_l2_policy();
@@ -95,12 +89,11 @@ k_linearize(const double4* __restrict__ xyt, const double2* __restrict__ cs, Row
   const int lr = wt.lr;
   const bool has_row = wt.valid && lr < L.nrows;
   int deg = 0;
-  double ox = 0, oy = 0, oth = 0, oc = 1, os = 0;
+  double ox = 0, oy = 0, oth = 0;
   if (has_row) {
     deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
     const double4 p = ld_keep4(xyt + L.row_lo + lr, pol.keep);
-    const double2 q = ld_keep2(cs + L.row_lo + lr, pol.keep);
-    ox = p.x; oy = p.y; oth = p.z; oc = q.x; os = q.y;
+    ox = p.x; oy = p.y; oth = p.z;
   }
   const int32_t* rp = wt.rp;
   double d00 = 0, d01 = 0, d02 = 0, d11 = 0, d12 = 0, d22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
@@ -109,10 +102,9 @@ k_linearize(const double4* __restrict__ xyt, const double2* __restrict__ cs, Row
     const bool side_b = (word & kFlagSideB) != 0;
     // edge frame: a = first endpoint, b = second
     const double xa = side_b ? pc.x : ox, ya = side_b ? pc.y : oy, tha = side_b ? pc.th : oth;
-    const double ca = side_b ? pc.c : oc, sa = side_b ? pc.s : os;
     const double xb = side_b ? ox : pc.x, yb = side_b ? oy : pc.y, thb = side_b ? oth : pc.th;
     EdgeTerms T;
-    edge_terms(xa, ya, tha, ca, sa, xb, yb, thb, r.tmx, r.tmy, r.thm, r.cm, r.sm, (word & kFlagDcs) != 0, P, T);
+    edge_terms(xa, ya, tha, xb, yb, thb, r.tmx, r.tmy, r.thm, (word & kFlagDcs) != 0, P, T);
     // diagonal block of the row pose and its gradient, accumulated in slot order
     d00 += T.U00; d01 += T.U01; d11 += T.U11;
     d02 += side_b ? T.sc0 : -T.e0;
@@ -143,14 +135,14 @@ k_linearize(const double4* __restrict__ xyt, const double2* __restrict__ cs, Row
   PoseRec poseA, poseB;
   if (deg > 0) w0 = ld_stream_u32(H.other + rp[0] + t, pol.stream);
   if (deg > 1) w1 = ld_stream_u32(H.other + rp[1] + t, pol.stream);
-  if (deg > 0) { recA = load_rec(H, (int64_t)rp[0] + t, pol.stream); poseA = gather_pose(xyt, cs, w0, pol.keep); }
+  if (deg > 0) { recA = load_rec(H, (int64_t)rp[0] + t, pol.stream); poseA = gather_pose(xyt, w0, pol.keep); }
   for (int k = 0; k < deg; k += 2) {
     uint32_t w2 = 0, w3 = 0;
-    if (k + 1 < deg) { recB = load_rec(H, (int64_t)rp[k + 1] + t, pol.stream); poseB = gather_pose(xyt, cs, w1, pol.keep); }
+    if (k + 1 < deg) { recB = load_rec(H, (int64_t)rp[k + 1] + t, pol.stream); poseB = gather_pose(xyt, w1, pol.keep); }
     if (k + 2 < deg) w2 = ld_stream_u32(H.other + rp[k + 2] + t, pol.stream);
     process(w0, recA, poseA, (int64_t)rp[k] + t);
     if (k + 1 >= deg) break;
-    if (k + 2 < deg) { recA = load_rec(H, (int64_t)rp[k + 2] + t, pol.stream); poseA = gather_pose(xyt, cs, w2, pol.keep); }
+    if (k + 2 < deg) { recA = load_rec(H, (int64_t)rp[k + 2] + t, pol.stream); poseA = gather_pose(xyt, w2, pol.keep); }
     if (k + 3 < deg) w3 = ld_stream_u32(H.other + rp[k + 3] + t, pol.stream);
     process(w1, recB, poseB, (int64_t)rp[k + 1] + t);
     w0 = w2; w1 = w3;
@@ -195,25 +187,22 @@ struct EdgeList {
   const double* tmx;
   const double* tmy;
   const double* thm;
-  const double* cm;
-  const double* sm;
   const uint8_t* dcs;   // 1 when the DCS functor applies to this edge
 };
 
 constexpr int kEdgeThreads = 256;
 
 __global__ void __launch_bounds__(kEdgeThreads)
-k_cost(const double4* __restrict__ xyt, const double2* __restrict__ cs, EdgeList E, int32_t e_lo, int32_t e_hi, Params P,
+k_cost(const double4* __restrict__ xyt, EdgeList E, int32_t e_lo, int32_t e_hi, Params P,
        double* partials, unsigned int* ticket, double* out) {
   double cost = 0.0;
   for (int64_t e = (int64_t)e_lo + (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x; e < e_hi;
        e += (int64_t)gridDim.x * kEdgeThreads) {
     const int32_t a = E.a[e], b = E.b[e];
     const double4 pa = xyt[a], pb = xyt[b];
-    const double2 qa = cs[a];
     double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
-    cost += edge_cost_terms(pa.x, pa.y, pa.z, qa.x, qa.y, pb.x, pb.y, pb.z, ld_stream(E.tmx + e), ld_stream(E.tmy + e),
-                            ld_stream(E.thm + e), ld_stream(E.cm + e), ld_stream(E.sm + e), E.dcs[e] != 0, P, q00, q01, dxw,
+    cost += edge_cost_terms(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ld_stream(E.tmx + e), ld_stream(E.tmy + e),
+                            ld_stream(E.thm + e), E.dcs[e] != 0, P, q00, q01, dxw,
                             dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1);
   }
   double s[1] = {cost};
@@ -221,16 +210,14 @@ k_cost(const double4* __restrict__ xyt, const double2* __restrict__ cs, EdgeList
 }
 
 __global__ void __launch_bounds__(kEdgeThreads)
-k_edge_eval(const double4* __restrict__ xyt, const double2* __restrict__ cs, EdgeList E, Params P, double* res, double* jac,
+k_edge_eval(const double4* __restrict__ xyt, EdgeList E, Params P, double* res, double* jac,
             double* psi, double* rho1) {
   const int64_t e = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   if (e >= E.n) return;
   const int32_t a = E.a[e], b = E.b[e];
   const double4 pa = xyt[a], pb = xyt[b];
-  const double2 qa = cs[a];
   EdgeLin L;
-  edge_linearize<true>(pa.x, pa.y, pa.z, qa.x, qa.y, pb.x, pb.y, pb.z, E.tmx[e], E.tmy[e], E.thm[e], E.cm[e], E.sm[e],
-                       E.dcs[e] != 0, P, L);
+  edge_linearize<true>(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, E.tmx[e], E.tmy[e], E.thm[e], E.dcs[e] != 0, P, L);
   if (res) { res[3 * e] = L.r0; res[3 * e + 1] = L.r1; res[3 * e + 2] = L.r2; }
   if (jac) {
     double* J = jac + 18 * e;
@@ -245,14 +232,10 @@ k_edge_eval(const double4* __restrict__ xyt, const double2* __restrict__ cs, Edg
 // ------------------------------------------------------------------------------------------------
 // pose upload helpers
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_poses(const double* __restrict__ xyt3, int32_t n, double4* xyt, double2* cs) {
+__global__ void k_pack_poses(const double* __restrict__ xyt3, int32_t n, double4* xyt) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double x = xyt3[3 * i], y = xyt3[3 * i + 1], th = xyt3[3 * i + 2];
-  double s, c;
-  sincos(th, &s, &c);
-  xyt[i] = make_double4(x, y, th, 0.0);
-  cs[i] = make_double2(c, s);
+  xyt[i] = make_double4(xyt3[3 * i], xyt3[3 * i + 1], xyt3[3 * i + 2], 0.0);   // 32-byte records: one sector per gather
 }
 __global__ void k_unpack_poses(const double4* __restrict__ xyt, int32_t n, double* xyt3) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,7 +466,7 @@ k_pack_step(const double* __restrict__ w, const double* __restrict__ g, int32_t 
 // candidate = x - w (delta = -w);  S_STEP_SQ = |w|^2;  S_XSQ = |candidate|^2 over parameter rows
 __global__ void __launch_bounds__(kVecThreads)
 k_apply_step(const double4* __restrict__ xyt, const double* __restrict__ w, const uint8_t* __restrict__ is_free,
-             int32_t row_lo, int32_t nrows, int64_t ldn, double4* cand_xyt, double2* cand_cs,
+             int32_t row_lo, int32_t nrows, int64_t ldn, double4* cand_xyt,
              double* partials, unsigned int* ticket, double* scal) {
   const int32_t i = blockIdx.x * kVecThreads + threadIdx.x;
   double ss = 0, xs = 0;
@@ -495,10 +478,7 @@ k_apply_step(const double4* __restrict__ xyt, const double* __restrict__ w, cons
       ss = fma(w0, w0, fma(w1, w1, w2 * w2));
       xs = fma(p.x, p.x, fma(p.y, p.y, p.z * p.z));
     }
-    double s, c;
-    sincos(p.z, &s, &c);
     cand_xyt[row_lo + i] = p;
-    cand_cs[row_lo + i] = make_double2(c, s);
   }
   double sv[2] = {ss, xs};
   grid_reduce_sum<2, kVecThreads>(sv, partials, ticket, scal + S_STEP_SQ);   // S_STEP_SQ, S_XSQ

@@ -108,8 +108,10 @@ __global__ void k_radix_scatter(const uint64_t* keys_in, const uint32_t* vals_in
 }
 
 // ---- half-edge generation ---------------------------------------------------------------------
-// key = row << 32 | col; val = edge << 1 | side.  Rows outside [row_lo,row_hi) or constant rows
-// are not generated (count pass with out == nullptr, then fill pass with offsets).
+// key = row << 32 | nonowner << 31 | col; val = edge << 1 | side.  Rows outside [row_lo,row_hi) or constant
+// rows are not generated.  "Owner" half-edges (col > row: the upper triangle, the blocks k_linearize stores;
+// also blocks whose partner row lives on another rank) sort before a row's other half-edges, so that in the
+// jagged-diagonal layout the early rounds are (almost) all owners and their block stores fill whole sectors.
 __global__ void k_halfedge_count(const int32_t* ea, const int32_t* eb, int32_t E, int32_t fixed, int32_t row_lo,
                                  int32_t row_hi, int32_t* cnt) {
   const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,8 +128,12 @@ __global__ void k_halfedge_fill(const int32_t* ea, const int32_t* eb, int32_t E,
   if (e >= E) return;
   const int32_t a = ea[e], b = eb[e];
   int32_t o = off[e];
-  if (a != fixed && a >= row_lo && a < row_hi) { keys[o] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; vals[o] = ((uint32_t)e << 1); ++o; }
-  if (b != fixed && b >= row_lo && b < row_hi) { keys[o] = ((uint64_t)(uint32_t)b << 32) | (uint32_t)a; vals[o] = ((uint32_t)e << 1) | 1u; }
+  auto key = [&](int32_t row, int32_t col) {
+    const bool owner = col != fixed && (row < col || col < row_lo || col >= row_hi);
+    return ((uint64_t)(uint32_t)row << 32) | (owner ? 0u : kKeyNonOwner) | (uint32_t)col;
+  };
+  if (a != fixed && a >= row_lo && a < row_hi) { keys[o] = key(a, b); vals[o] = ((uint32_t)e << 1); ++o; }
+  if (b != fixed && b >= row_lo && b < row_hi) { keys[o] = key(b, a); vals[o] = ((uint32_t)e << 1) | 1u; }
 }
 
 // degree of every pose over ALL edges (decides which poses are parameters at all)
@@ -206,7 +212,7 @@ __global__ void k_upper_flag(const uint64_t* keys, int32_t nh, int32_t fixed, in
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const uint64_t k = keys[i];
-  const int32_t row = (int32_t)(k >> 32), col = (int32_t)(k & 0xFFFFFFFFu);
+  const int32_t row = (int32_t)(k >> 32), col = (int32_t)(k & kIdxMask);
   const bool first = (i == 0) || (keys[i - 1] != k);
   flag[i] = (first && row < col && col != fixed) ? 1 : 0;
 }

@@ -8,7 +8,8 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def lib_path():
-    return os.path.join(_PKG, "libdcs_b200.so")
+    # DCS_B200_LIB: development override (kernel variants); the default is the in-tree build
+    return os.environ.get("DCS_B200_LIB") or os.path.join(_PKG, "libdcs_b200.so")
 
 
 def host_lib_path():
