@@ -79,7 +79,7 @@ __device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, 
 // off-diagonal block per edge, written by the half-edge whose row is the smaller endpoint: kFlagOwner),
 // the diagonal blocks and the gradient.  The mirrored (lower) copies the SpMV's full row storage wants
 // are filled by k_mirror as part of the linear-solver setup.
-__global__ void __launch_bounds__(kRowsPerBlock, 16)
+__global__ void __launch_bounds__(kRowsPerBlock, 20)
 k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
             double* __restrict__ Hoff, double* __restrict__ Hdiag, double* __restrict__ grad,
             WarpRedWs red, double* scal) {
