@@ -181,13 +181,15 @@ def main():
     value = g.n_edges / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the C-ABI with host buffers: H2D poses, launch, D2H cost + gradient, every step
-    x = np.array(g.pose_xyt)
+    x = D.pinned_empty(g.pose_xyt.shape)           # page-locked host buffers, as the contract asks
+    x[...] = g.pose_xyt
+    grad_out = D.pinned_empty(g.pose_xyt.shape)
     for _ in range(3):
-        s.linearize(x)
+        s.linearize(x, out=grad_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        cost, grad = s.linearize(x)
+        cost, grad = s.linearize(x, out=grad_out)
     e2e_s = time.perf_counter() - t0
     barrier()
     if dist:

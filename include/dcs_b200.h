@@ -184,6 +184,12 @@ int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double
 int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* summary,
               dcs_iteration* trace, int32_t trace_cap);
 
+/* Page-locked host buffers (cudaHostAlloc).  Pose / gradient arrays handed to dcs_linearize, dcs_evaluate and
+ * dcs_solve may live anywhere; when they are page-locked the library DMAs straight from / into them instead of
+ * staging through its own pinned bounce buffer. */
+void* dcs_host_alloc(uint64_t bytes);
+void dcs_host_free(void* p);
+
 /* Last CUDA / NCCL error text for this thread ("" if none). */
 const char* dcs_last_error(void);
 

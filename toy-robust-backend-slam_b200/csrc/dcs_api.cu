@@ -317,10 +317,20 @@ int read_scalars(dcs_handle* h) {
   return DCS_OK;
 }
 
-// host N x 3 poses -> device packed poses (+ cos/sin)
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// host N x 3 poses -> device packed poses
 int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt) {
-  std::memcpy(h->h_pin3, pose_xyt, (size_t)h->N * 3 * sizeof(double));
-  CK(cudaMemcpyAsync(h->stage3.p, h->h_pin3, (size_t)h->N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const double* src = pose_xyt;
+  if (!is_pinned(pose_xyt)) {       // pageable caller memory: bounce through the handle's pinned buffer
+    std::memcpy(h->h_pin3, pose_xyt, (size_t)h->N * 3 * sizeof(double));
+    src = h->h_pin3;
+  }
+  CK(cudaMemcpyAsync(h->stage3.p, src, (size_t)h->N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   LAUNCH(k_pack_poses, cdiv(h->N, 256), 256, h->stream, h->stage3.p, h->N, xyt);
   return DCS_OK;
 }
@@ -461,6 +471,13 @@ void dcs_options_default(dcs_options* o) {
   o->world = 1;
   o->nccl_unique_id = nullptr;
 }
+
+void* dcs_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; cudaGetLastError(); return nullptr; }
+  return p;
+}
+void dcs_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 const char* dcs_version(void) { return "dcs_b200 0.1 (sm_100a)"; }
 const char* dcs_last_error(void) { return g_err.c_str(); }
@@ -708,16 +725,16 @@ int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* g
   CK(cudaSetDevice(h->dev));
   CKS(upload_poses(h, pose_xyt, h->xyt.p));
   CKS(linearize(h, h->xyt.p));
+  const bool direct = gradient && is_pinned(gradient);
+  if (gradient && h->world > 1) std::memset(gradient, 0, (size_t)h->N * 24);
   if (gradient && h->nrows > 0) {
     LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->nrows, h->ldn, h->stage3.p);
-    CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)h->nrows * 24, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(direct ? gradient + 3 * (size_t)h->row_lo : h->h_pin3, h->stage3.p, (size_t)h->nrows * 24,
+                       cudaMemcpyDeviceToHost, h->stream));
   }
   CKS(read_scalars(h));
   if (cost) *cost = h->h_scal[S_COST];
-  if (gradient) {
-    if (h->world > 1) std::memset(gradient, 0, (size_t)h->N * 24);
-    std::memcpy(gradient + 3 * (size_t)h->row_lo, h->h_pin3, (size_t)h->nrows * 24);
-  }
+  if (gradient && !direct) std::memcpy(gradient + 3 * (size_t)h->row_lo, h->h_pin3, (size_t)h->nrows * 24);
   return DCS_OK;
 }
 

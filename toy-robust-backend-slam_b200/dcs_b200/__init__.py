@@ -7,8 +7,8 @@ imports anything from oracle/.  Loading fails loudly if libdcs_b200.so has not b
 library's CUDA error when no B200 is usable: there is no CPU fallback.
 """
 from .capi import (DcsError, Graph, Options, Solver, Summary, device_count, launch_count, lib_path,
-                   host_lib_path, nccl_unique_id, partition, version, load_library, load_host_library,
+                   host_lib_path, nccl_unique_id, partition, pinned_empty, version, load_library, load_host_library,
                    DECLARED_SYMBOLS)
 
 __all__ = ["DcsError", "Graph", "Options", "Solver", "Summary", "device_count", "launch_count", "lib_path",
-           "host_lib_path", "nccl_unique_id", "partition", "version", "load_library", "load_host_library", "DECLARED_SYMBOLS"]
+           "host_lib_path", "nccl_unique_id", "partition", "pinned_empty", "version", "load_library", "load_host_library", "DECLARED_SYMBOLS"]

@@ -60,7 +60,8 @@ class Summary(C.Structure):
 # every symbol include/dcs_b200.h declares (tests check the .so exports all of them)
 DECLARED_SYMBOLS = ["dcs_options_default", "dcs_version", "dcs_device_count", "dcs_partition", "dcs_nccl_unique_id", "dcs_create",
                     "dcs_destroy", "dcs_evaluate", "dcs_linearize", "dcs_linearize_resident", "dcs_cost",
-                    "dcs_get_pattern", "dcs_get_hessian", "dcs_pcg_solve", "dcs_solve", "dcs_last_error",
+                    "dcs_get_pattern", "dcs_get_hessian", "dcs_pcg_solve", "dcs_solve", "dcs_host_alloc", "dcs_host_free",
+                    "dcs_last_error",
                     "dcs_launch_count"]
 
 _lib = None
@@ -96,6 +97,10 @@ def load_library():
     lib.dcs_pcg_solve.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     lib.dcs_solve.argtypes = [vp, vp, C.POINTER(Summary), C.POINTER(Iteration), C.c_int32]
     lib.dcs_nccl_unique_id.argtypes = [vp]
+    lib.dcs_host_alloc.restype = C.c_void_p
+    lib.dcs_host_alloc.argtypes = [C.c_uint64]
+    lib.dcs_host_free.argtypes = [C.c_void_p]
+    lib.dcs_host_free.restype = None
     _lib = lib
     return lib
 
@@ -152,6 +157,25 @@ def partition(n_poses, n_edges, rank, world):
     if rc:
         raise DcsError(rc, "dcs_partition", "bad argument")
     return tuple(out)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory from dcs_host_alloc (kept alive by the array's base object)."""
+    lib = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.dcs_host_alloc(max(n, 8))
+    if not ptr:
+        raise DcsError(2, "dcs_host_alloc", lib.dcs_last_error().decode())
+
+    class _Owner:
+        def __init__(self, p): self.p = p
+        def __del__(self):
+            try: lib.dcs_host_free(self.p)
+            except Exception: pass
+
+    buf = (C.c_char * n).from_address(ptr)
+    buf._owner = _Owner(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 def nccl_unique_id():
@@ -298,10 +322,10 @@ class Solver:
                  "dcs_evaluate")
         return dict(cost=cost.value, residuals=r, jacobians=J, psi=psi, rho1=rho1, gradient=g)
 
-    def linearize(self, pose_xyt, want_gradient=True):
+    def linearize(self, pose_xyt, want_gradient=True, out=None):
         x = np.ascontiguousarray(pose_xyt, dtype=np.float64)
         cost = C.c_double()
-        g = np.empty((self.graph.n_poses, 3)) if want_gradient else None
+        g = out if out is not None else (np.empty((self.graph.n_poses, 3)) if want_gradient else None)
         self._ck(self.lib.dcs_linearize(self.h, _ptr(x), C.byref(cost), _ptr(g)), "dcs_linearize")
         return cost.value, g
 
