@@ -163,6 +163,23 @@ __global__ void k_export_upper(const uint64_t* __restrict__ keys, const int32_t*
   for (int c = 0; c < 9; ++c) o[c] = acc[c];
 }
 
+// development probe: K1's memory traffic as a flat, dependency-free stream (one thread per half-edge slot)
+__global__ void k_dbg_flat(const uint32_t* __restrict__ other, const double* __restrict__ tmx, const double* __restrict__ tmy,
+                           const double* __restrict__ thm, const double4* __restrict__ xyt, int32_t nh, int64_t ldh, double* Hoff,
+                           int mode) {
+  const L2Policy pol = make_l2_policy();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const uint32_t w = ld_stream_u32(other + i, pol.stream);
+  double a = ld_stream(tmx + i, pol.stream), b = ld_stream(tmy + i, pol.stream), c = ld_stream(thm + i, pol.stream);
+  if (mode & 1) { const double4 p = ld_keep4(xyt + (w & kIdxMask), pol.keep); a += p.x; b += p.y; c += p.z; }
+  if ((mode & 2) && ((w & kFlagOwner) || (mode & 4))) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st_stream(Hoff + (int64_t)k * ldh + i, a + k * b + c, pol.stream);
+  }
+  if (!(mode & 2) && a + b + c == 1.2345e300) Hoff[i] = a;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -750,6 +767,20 @@ int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total) {
   if (ms_total) *ms_total = ms;
   CK(cudaGetLastError());
   return DCS_OK;
+}
+
+// development probe (not part of the public header): time the flat traffic kernel; returns us per launch
+extern "C" double dcs_debug_flat(dcs_handle* h, int mode, int repeats) {
+  cudaSetDevice(h->dev);
+  const int grid = cdiv(h->nh, 256);
+  for (int i = 0; i < 3; ++i) k_dbg_flat<<<grid, 256, 0, h->stream>>>(h->h_other.p, h->h_tmx.p, h->h_tmy.p, h->h_thm.p, h->xyt.p, h->nh, h->ldh, h->Hoff.p, mode);
+  cudaEventRecord(h->ev0, h->stream);
+  for (int i = 0; i < repeats; ++i) k_dbg_flat<<<grid, 256, 0, h->stream>>>(h->h_other.p, h->h_tmx.p, h->h_tmy.p, h->h_thm.p, h->xyt.p, h->nh, h->ldh, h->Hoff.p, mode);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  return 1e3 * ms / repeats;
 }
 
 int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost) {
