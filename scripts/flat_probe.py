@@ -9,3 +9,7 @@ lib = D.load_library(); lib.dcs_debug_flat.restype = C.c_double; lib.dcs_debug_f
 print("k_linearize us", 1e3 * s.linearize_resident(20) / 20)
 for mode, name in ((0, "stream loads only (28 B x 8M)"), (1, "+ gather pose"), (3, "+ gather + owner-only 9 stores"), (7, "+ gather + all-lane 9 stores"), (2, "loads + owner stores, no gather"), (6, "loads + all stores, no gather")):
     print(f"mode {mode}: {name}: {lib.dcs_debug_flat(s.h, mode, 20):.1f} us")
+
+# occupancy experiment: cap resident CTAs (256 threads = 8 warps each) with dynamic shared memory
+for kb, ctas in ((0, 8), (56, 4), (75, 3), (110, 2), (200, 1)):
+    print(f"mode 3 with {kb} KB smem/CTA (~{ctas} CTAs = {8*ctas} warps per SM): {lib.dcs_debug_flat(s.h, 3 | (kb << 8), 20):.1f} us")

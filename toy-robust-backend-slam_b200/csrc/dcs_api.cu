@@ -221,6 +221,7 @@ struct dcs_handle {
   double lin_cost = 0, lin_gsq = 0, lin_gmax = 0;
   bool lin_scal_pending = false;           // per-rank scalars not folded into h_scal yet
   DevBuf<unsigned int> red_tickets;        // [ngroups] group tickets + [1] global ticket
+  DevBuf<double> task_part;                // [3][ntasks] per-task partial sums of the row-owner kernels
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
@@ -362,7 +363,9 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 // K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
 int linearize(dcs_handle* h, const double4* xyt) {
   LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
-         h->grad.p, h->red(), h->scal.p);
+         h->grad.p, h->task_part.p);
+  k_fold_tasks<2, 1><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0);
+  ++g_launches;
   if (h->world > 1) {   // one collective: every rank's (cost, |g|^2, |g|_inf); folded on the host in rank order
     CKN(nccl_api().AllGather(h->scal.p + S_COST, h->rank_scal.p, 4, ncclDouble, h->comm, h->stream));
     h->lin_scal_pending = true;
@@ -391,8 +394,9 @@ int cost_only(dcs_handle* h, const double4* xyt, int slot) {
 
 // one PCG iteration on the stream (capturable)
 int pcg_iteration(dcs_handle* h, const double* D) {
-  LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->red(),
-         h->scal.p, (int)S_PQ, 1);
+  LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->task_part.p);
+  k_fold_tasks<1, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1);
+  ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
   LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, h->row_lo, h->nrows, h->ldn, h->w.p,
          h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
@@ -433,12 +437,12 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
       CK(cudaGraphDestroy(g));
       h->pcg_graph_iters = batch;
       h->pcg_graph_D = h->Adiag.p;
-      g_launches -= 3LL * batch;   // capture does not launch
+      g_launches -= 4LL * batch;   // capture does not launch
     }
     const double target = h->opt.pcg_rel_tol * h->opt.pcg_rel_tol * rr0;
     while (iters < h->opt.pcg_max_iter) {
       CK(cudaGraphLaunch(h->pcg_graph, h->stream));
-      g_launches += 3LL * batch;
+      g_launches += 4LL * batch;
       iters += batch;
       CKS(read_scalars(h));
       rr = h->h_scal[S_RR];
@@ -687,6 +691,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->partials.alloc_zero(4 * max_grid));
   CK(h->scal.alloc_zero(S_COUNT));
   CK(h->tickets.alloc_zero(8));
+  CK(h->task_part.alloc_zero((size_t)3 * h->nblk));
   CK(h->red_part.alloc_zero((size_t)3 * h->nblk));
   CK(h->red_gpart.alloc_zero((size_t)3 * cdiv(h->nblk, kRedGroup)));
   CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1));
@@ -992,8 +997,9 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
     CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
     CKS(ensure_mirror(h));
-    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->red(),
-           h->scal.p, (int)S_WHW, 0);
+    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->task_part.p);
+    k_fold_tasks<1, 0><<<1, kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + S_WHW, h->scal.p, 0);
+    ++g_launches;
     CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
     // candidate = x - w
     LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->cand_xyt.p,

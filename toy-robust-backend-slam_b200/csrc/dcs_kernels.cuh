@@ -82,7 +82,7 @@ __device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, 
 __global__ void __launch_bounds__(kRowsPerBlock, 20)
 k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
             double* __restrict__ Hoff, double* __restrict__ Hdiag, double* __restrict__ grad,
-            WarpRedWs red, double* scal) {
+            double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
   const WarpTask wt = warp_task(L);
   const int t = wt.rank;
@@ -152,8 +152,51 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     Hdiag[3 * L.ldn + lr] = d11; Hdiag[4 * L.ldn + lr] = d12; Hdiag[5 * L.ldn + lr] = d22;
     grad[0 * L.ldn + lr] = g0; grad[1 * L.ldn + lr] = g1; grad[2 * L.ldn + lr] = g2;
   }
-  const double red_in[3] = {cost, fma(g0, g0, fma(g1, g1, g2 * g2)), fmax(fabs(g0), fmax(fabs(g1), fabs(g2)))};
-  warp_grid_reduce<2, 1>(red_in, red, scal + S_COST);   // S_COST, S_GSQ (sums), S_GMAX (max)
+  // per-task partials (no fence, no ticket: a __threadfence per 32-row task cost ~7 k cycles of its ~40 k);
+  // k_fold_tasks adds them in task order
+  double r0 = cost, r1 = fma(g0, g0, fma(g1, g1, g2 * g2)), r2 = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const size_t n = gridDim.x;
+    task_part[blockIdx.x] = r0; task_part[n + blockIdx.x] = r1; task_part[2 * n + blockIdx.x] = r2;
+  }
+}
+
+// Deterministic fold of per-task partials (K sums then M maxima, each n long) in task order.
+// `rotate_rz`: S_RZ <- S_RZ_NEXT (PCG scalar rotation, see k_pcg_direction).
+constexpr int kFoldThreads = 1024;
+template <int K, int M>
+__global__ void __launch_bounds__(kFoldThreads)
+k_fold_tasks(const double* __restrict__ part, int n, double* out, double* scal, int rotate_rz) {
+  __shared__ double s_red[kFoldThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < K + M; ++k) {
+    const bool is_sum = k < K;
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += kFoldThreads) {
+      const double y = part[(size_t)k * n + i];
+      a = is_sum ? a + y : fmax(a, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, a, o);
+      a = is_sum ? a + y : fmax(a, y);
+    }
+    __syncthreads();
+    if (lane == 0) s_red[wid] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kFoldThreads / 32; ++w) t = is_sum ? t + s_red[w] : fmax(t, s_red[w]);
+      out[k] = t;
+    }
+  }
+  if (threadIdx.x == 0 && rotate_rz) scal[S_RZ] = scal[S_RZ_NEXT];
 }
 
 // Linear-solver setup: the SpMV walks full rows, so every non-owner slot receives the transpose of its
@@ -306,7 +349,7 @@ __global__ void k_precond(const double* __restrict__ Hdiag, const double* __rest
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowsPerBlock)
 k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__ other, const double* __restrict__ Hoff,
-       const double* __restrict__ D, double* __restrict__ q, WarpRedWs red, double* scal, int dot_slot, int rotate_rz) {
+       const double* __restrict__ D, double* __restrict__ q, double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
   const WarpTask wt = warp_task(L);
   const int t = wt.rank;
@@ -356,12 +399,9 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
     q[0 * L.ldn + lr] = y0; q[1 * L.ldn + lr] = y1; q[2 * L.ldn + lr] = y2;
     dot = fma(p.x, y0, fma(p.y, y1, p.z * y2));
   }
-  const double red_in[1] = {dot};
-  warp_grid_reduce<1, 0>(red_in, red, scal + dot_slot);
-  if (rotate_rz && threadIdx.x == 0 && blockIdx.x == 0) {
-    // Safe: S_RZ / S_RZ_NEXT are not read by any thread of this kernel.
-    scal[S_RZ] = scal[S_RZ_NEXT];
-  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) task_part[blockIdx.x] = dot;
 }
 
 // ------------------------------------------------------------------------------------------------
