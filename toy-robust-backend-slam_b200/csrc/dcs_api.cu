@@ -174,10 +174,28 @@ __global__ void k_dbg_flat(const uint32_t* __restrict__ other, const double* __r
   double a = ld_stream(tmx + i, pol.stream), b = ld_stream(tmy + i, pol.stream), c = ld_stream(thm + i, pol.stream);
   if (mode & 1) { const double4 p = ld_keep4(xyt + (w & kIdxMask), pol.keep); a += p.x; b += p.y; c += p.z; }
   if ((mode & 2) && ((w & kFlagOwner) || (mode & 4))) {
+    if (mode & 8) {         // tile-interleaved: [slot/32][9][32]
+      double* o = Hoff + (i >> 5) * 288 + (i & 31);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) st_stream(Hoff + (int64_t)k * ldh + i, a + k * b + c, pol.stream);
+      for (int k = 0; k < 9; ++k) st_stream(o + k * 32, a + k * b + c, pol.stream);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st_stream(Hoff + (int64_t)k * ldh + i, a + k * b + c, pol.stream);
+    }
   }
   if (!(mode & 2) && a + b + c == 1.2345e300) Hoff[i] = a;
+}
+
+// development probe: scatter-add cost of an edge-centric assembly (18 fp64 reductions per edge into the
+// diagonal blocks / gradient of the two endpoints)
+__global__ void k_dbg_atomic(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, int32_t E, int64_t ldn, double* acc, int nper) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int32_t a = ea[e], b = eb[e];
+  for (int c = 0; c < nper; ++c) {
+    atomicAdd(acc + (int64_t)c * ldn + a, 1.0 + c);
+    atomicAdd(acc + (int64_t)c * ldn + b, 2.0 + c);
+  }
 }
 
 }  // namespace
@@ -785,6 +803,23 @@ extern "C" double dcs_debug_flat(dcs_handle* h, int mode, int repeats) {
   cudaEventSynchronize(h->ev1);
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  return 1e3 * ms / repeats;
+}
+
+extern "C" double dcs_debug_atomic(dcs_handle* h, int nper, int repeats) {
+  cudaSetDevice(h->dev);
+  double* acc = nullptr;
+  cudaMalloc(&acc, (size_t)9 * h->ldn * 8);
+  cudaMemset(acc, 0, (size_t)9 * h->ldn * 8);
+  const int grid = cdiv(h->E, 256);
+  k_dbg_atomic<<<grid, 256, 0, h->stream>>>(h->ea.p, h->eb.p, h->E, h->ldn, acc, nper);
+  cudaEventRecord(h->ev0, h->stream);
+  for (int i = 0; i < repeats; ++i) k_dbg_atomic<<<grid, 256, 0, h->stream>>>(h->ea.p, h->eb.p, h->E, h->ldn, acc, nper);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  cudaFree(acc);
   return 1e3 * ms / repeats;
 }
 
