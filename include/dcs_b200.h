@@ -85,6 +85,9 @@ typedef struct dcs_options {
   double pcg_rel_tol;             /* stop when |r|_2 <= pcg_rel_tol * |rhs|_2            */
   int32_t pcg_max_iter;
   int32_t pcg_check_every;        /* iterations per graph launch between host checks     */
+  int32_t preconditioner;         /* 0: 3x3 block-Jacobi; 1 (default): block-Jacobi over chain segments of 32 poses
+                                   * (each block = the block-tridiagonal odometry-chain part of the segment,
+                                   * factorised exactly once per LM iteration)                                    */
   /* execution */
   int32_t device;                 /* CUDA device ordinal                                 */
   int32_t verbose;                /* 1: Ceres-style progress table on stdout             */

@@ -170,14 +170,16 @@ def test_hub_pose_with_many_loops():
     assert np.abs(ev["gradient"] - ref["gradient"]).max() <= 1e-11 * np.abs(ref["gradient"]).max()
 
 
+@pytest.mark.parametrize("precond", [0, 1])
 @pytest.mark.parametrize("name,dcs", [("INTEL_50_seed1", 1), ("M3500_100_seed1", 0)])
-def test_pcg_matches_exact_cholesky(name, dcs):
+def test_pcg_matches_exact_cholesky(name, dcs, precond):
+    """precond 0: 3x3 block-Jacobi; 1: block-Jacobi over 32-pose chain segments (block-tridiagonal, exact)."""
     g, z = load_case(name)
     ora = O.Oracle(g, dcs_on=bool(dcs))
     rhs = ora.evaluate()["gradient"]
     for lam_v in (1e-2, 1e-6):
         lam = np.full((g.n_poses, 3), lam_v)
-        with D.Solver(g, dcs_on=bool(dcs), pcg_rel_tol=1e-13) as s:
+        with D.Solver(g, dcs_on=bool(dcs), pcg_rel_tol=1e-13, preconditioner=precond) as s:
             s.linearize(g.pose_xyt)
             w, it, rel = s.pcg_solve(lam, rhs)
         wo = ora.linear_solve(lam, rhs)
@@ -215,6 +217,19 @@ def test_full_lm_solve_matches_oracle_trace(name, dcs):
         bogus = g.kind == 2
         if bogus.any():
             assert (psi[bogus] < 0.5).mean() > 0.9          # DCS switches the injected loops off
+
+
+def test_chain_preconditioner_cuts_iterations_and_keeps_the_trace():
+    g, z = load_case("M3500_100_seed1")
+    res = {}
+    for pc in (0, 1):
+        with D.Solver(g, dcs_on=True, preconditioner=pc, max_num_iterations=12) as s:
+            x, sm, tr = s.solve()
+        res[pc] = (sm.total_pcg_iterations, [t.step_is_successful for t in tr], sm.final_cost, x)
+    assert res[0][1] == res[1][1] == list(z["trace_ok_dcs1"][:13])
+    assert abs(res[0][2] - res[1][2]) <= 1e-10 * res[0][2]
+    assert np.abs(res[0][3] - res[1][3]).max() < 1e-7
+    assert res[1][0] < 0.75 * res[0][0], (res[0][0], res[1][0])
 
 
 def test_solve_is_bit_reproducible():

@@ -69,10 +69,12 @@ struct DevBuf {
     if (count == 0) return cudaSuccess;
     return cudaMalloc(&p, count * sizeof(T));
   }
-  cudaError_t alloc_zero(size_t count) {
+  // zero-fill ordered on the handle's (non-blocking) stream: a plain cudaMemset goes to the legacy default stream,
+  // which that stream does not order against
+  cudaError_t alloc_zero(size_t count, cudaStream_t st) {
     cudaError_t e = alloc(count);
     if (e != cudaSuccess || count == 0) return e;
-    return cudaMemset(p, 0, count * sizeof(T));
+    return cudaMemsetAsync(p, 0, count * sizeof(T), st);
   }
 };
 
@@ -240,6 +242,9 @@ struct dcs_handle {
   bool lin_scal_pending = false;           // per-rank scalars not folded into h_scal yet
   DevBuf<unsigned int> red_tickets;        // [ngroups] group tickets + [1] global ticket
   DevBuf<double> task_part;                // [3][ntasks] per-task partial sums of the row-owner kernels
+  DevBuf<float> chL, chS;                  // chain-segment preconditioner factors (fp32), step-major
+  DevBuf<int32_t> chain_idx, chain_cnt;    // (r, r+1) entries in the sorted half-edge list
+  int ntiles = 0;                          // 1024-pose tiles of the chain preconditioner
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
@@ -416,8 +421,15 @@ int pcg_iteration(dcs_handle* h, const double* D) {
   k_fold_tasks<1, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1);
   ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
-  LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, h->row_lo, h->nrows, h->ldn, h->w.p,
-         h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
+  if (h->opt.preconditioner == 1) {
+    LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
+           h->row_lo, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    k_fold_tasks<2, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0);
+    ++g_launches;
+  } else {
+    LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, h->row_lo, h->nrows, h->ldn, h->w.p,
+           h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
+  }
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
   LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->scal.p);
   CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
@@ -431,6 +443,14 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
   CKS(ensure_mirror(h));
   LAUNCH(k_precond, h->vec_grid(), 256, h->stream, h->Hdiag.p, h->lmdiag.p, h->scale.p, h->is_free.p, h->nrows, h->ldn, inv_radius,
          lambda_explicit, h->Adiag.p, h->Minv.p);
+  if (h->opt.preconditioner == 1) {
+    LAUNCH(k_chain_factor, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->nrows, h->ldn,
+           h->ldh, h->chL.p, h->chS.p);
+    LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->row_lo, h->nrows,
+           h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    k_fold_tasks<2, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0);
+    ++g_launches;
+  } else
   LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->w.p, h->r.p,
          h->z.p, h->p4.p, h->partials.p, h->tickets.p + 4, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
@@ -455,12 +475,12 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
       CK(cudaGraphDestroy(g));
       h->pcg_graph_iters = batch;
       h->pcg_graph_D = h->Adiag.p;
-      g_launches -= 4LL * batch;   // capture does not launch
+      g_launches -= (h->opt.preconditioner == 1 ? 5LL : 4LL) * batch;   // capture does not launch
     }
     const double target = h->opt.pcg_rel_tol * h->opt.pcg_rel_tol * rr0;
     while (iters < h->opt.pcg_max_iter) {
       CK(cudaGraphLaunch(h->pcg_graph, h->stream));
-      g_launches += 4LL * batch;
+      g_launches += (h->opt.preconditioner == 1 ? 5LL : 4LL) * batch;
       iters += batch;
       CKS(read_scalars(h));
       rr = h->h_scal[S_RR];
@@ -504,6 +524,7 @@ void dcs_options_default(dcs_options* o) {
   o->pcg_rel_tol = 1e-12;
   o->pcg_max_iter = 200000;
   o->pcg_check_every = 32;
+  o->preconditioner = 1;
   o->device = 0;
   o->verbose = 0;
   o->rank = 0;
@@ -634,13 +655,13 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
                     h->e_dcs.p);
 
   // ---- K0: half-edges, sort, CSR, jagged-diagonal re-layout ---------------------------------------
-  CK(h->deg_all.alloc_zero((size_t)h->Npad));
+  CK(h->deg_all.alloc_zero((size_t)h->Npad, st));
   if (E > 0) LAUNCH(k_pose_degree, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->deg_all.p);
-  CK(h->is_free.alloc_zero((size_t)h->ldn));
+  CK(h->is_free.alloc_zero((size_t)h->ldn, st));
   if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->is_free.p);
 
   DevBuf<int32_t> he_off;
-  CK(he_off.alloc_zero((size_t)E + 1));
+  CK(he_off.alloc_zero((size_t)E + 1, st));
   const int32_t row_hi = h->row_lo + h->nrows;
   if (E > 0) LAUNCH(k_halfedge_count, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->fixed, h->row_lo, row_hi, he_off.p);
   CKS(scan_exclusive(he_off.p, (int64_t)E + 1, st));
@@ -653,7 +674,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->vals.alloc((size_t)std::max(nh, 1)));
   if (E > 0) LAUNCH(k_halfedge_fill, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->fixed, h->row_lo, row_hi, he_off.p, h->keys.p, h->vals.p);
   const int nb = bits_for(std::max(N, 2));
-  CKS(radix_sort(h->keys, h->vals, nh, nb, nb, st));
+  CKS(radix_sort(h->keys, h->vals, nh, 28, nb, st));   // column word: 27 index bits + the owner-order bit
 
   CK(h->row_ptr.alloc((size_t)h->ldn + 1));
   {
@@ -662,7 +683,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     LAUNCH(k_row_ptr, cdiv(rows + 1, 256), 256, st, h->keys.p, nh, h->row_lo, rows, h->row_ptr.p);
   }
   CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
-  CK(h->rp_off.alloc_zero((size_t)h->nwin + 1));
+  CK(h->rp_off.alloc_zero((size_t)h->nwin + 1, st));
   LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
   CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nwin + 1, st));
   int32_t n_rounds = 0;
@@ -675,7 +696,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
                      h->round_ptr.p, h->slot.p);
 
   const size_t HH = (size_t)h->ldh;
-  CK(h->h_other.alloc_zero(HH)); CK(h->h_tmx.alloc_zero(HH)); CK(h->h_tmy.alloc_zero(HH)); CK(h->h_thm.alloc_zero(HH));
+  CK(h->h_other.alloc_zero(HH, st)); CK(h->h_tmx.alloc_zero(HH, st)); CK(h->h_tmy.alloc_zero(HH, st)); CK(h->h_thm.alloc_zero(HH, st));
   CK(h->mirror_src.alloc((size_t)std::max(nh, 1)));
   if (nh > 0) {
     DevBuf<int32_t> edge_slot;
@@ -689,7 +710,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   }
 
   // unique upper pattern (parity hook)
-  CK(h->up_flag.alloc_zero((size_t)nh + 1)); CK(h->up_scan.alloc_zero((size_t)nh + 1));
+  CK(h->up_flag.alloc_zero((size_t)nh + 1, st)); CK(h->up_scan.alloc_zero((size_t)nh + 1, st));
   if (nh > 0) {
     LAUNCH(k_upper_flag, cdiv(nh, 256), 256, st, h->keys.p, nh, h->fixed, h->up_flag.p);
     CK(cudaMemcpyAsync(h->up_scan.p, h->up_flag.p, (size_t)(nh + 1) * 4, cudaMemcpyDeviceToDevice, st));
@@ -700,22 +721,26 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
 
   // ---- state --------------------------------------------------------------------------------------
   const size_t NP = (size_t)h->Npad, LN = (size_t)h->ldn;
-  CK(h->xyt.alloc_zero(NP)); CK(h->cand_xyt.alloc_zero(NP)); CK(h->p4.alloc_zero(NP));
-  CK(h->Hoff.alloc_zero(9 * HH)); CK(h->Hdiag.alloc_zero(6 * LN)); CK(h->grad.alloc_zero(3 * LN));
-  CK(h->scale.alloc_zero(3 * LN)); CK(h->lmdiag.alloc_zero(3 * LN)); CK(h->Adiag.alloc_zero(6 * LN)); CK(h->Minv.alloc_zero(6 * LN));
-  CK(h->w.alloc_zero(3 * LN)); CK(h->r.alloc_zero(3 * LN)); CK(h->q.alloc_zero(3 * LN)); CK(h->z.alloc_zero(3 * LN));
-  CK(h->lambda_tmp.alloc_zero(3 * LN)); CK(h->rhs_tmp.alloc_zero(3 * LN));
+  CK(h->xyt.alloc_zero(NP, st)); CK(h->cand_xyt.alloc_zero(NP, st)); CK(h->p4.alloc_zero(NP, st));
+  CK(h->Hoff.alloc_zero(9 * HH, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
+  CK(h->scale.alloc_zero(3 * LN, st)); CK(h->lmdiag.alloc_zero(3 * LN, st)); CK(h->Adiag.alloc_zero(6 * LN, st)); CK(h->Minv.alloc_zero(6 * LN, st));
+  CK(h->w.alloc_zero(3 * LN, st)); CK(h->r.alloc_zero(3 * LN, st)); CK(h->q.alloc_zero(3 * LN, st)); CK(h->z.alloc_zero(3 * LN, st));
+  CK(h->lambda_tmp.alloc_zero(3 * LN, st)); CK(h->rhs_tmp.alloc_zero(3 * LN, st));
   const size_t max_grid = (size_t)std::max<int64_t>({(int64_t)h->nblk, (int64_t)h->vec_grid(), 148 * 8});
-  CK(h->partials.alloc_zero(4 * max_grid));
-  CK(h->scal.alloc_zero(S_COUNT));
-  CK(h->tickets.alloc_zero(8));
-  CK(h->task_part.alloc_zero((size_t)3 * h->nblk));
-  CK(h->red_part.alloc_zero((size_t)3 * h->nblk));
-  CK(h->red_gpart.alloc_zero((size_t)3 * cdiv(h->nblk, kRedGroup)));
-  CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1));
-  CK(h->stage3.alloc_zero((size_t)N * 3));
+  CK(h->partials.alloc_zero(4 * max_grid, st));
+  CK(h->scal.alloc_zero(S_COUNT, st));
+  CK(h->tickets.alloc_zero(8, st));
+  h->ntiles = (int)(h->ldn / kChainTile);
+  CK(h->chL.alloc_zero(9 * LN, st)); CK(h->chS.alloc_zero(6 * LN, st));
+  CK(h->chain_idx.alloc_zero(LN, st)); CK(h->chain_cnt.alloc_zero(LN, st));
+  if (h->nrows > 0) LAUNCH(k_chain_entries, cdiv(h->nrows, 256), 256, st, h->keys.p, nh, h->row_lo, h->nrows, h->chain_idx.p, h->chain_cnt.p);
+  CK(h->task_part.alloc_zero((size_t)3 * std::max(h->nblk, (int32_t)(h->ldn / kChainTile) + 1), st));
+  CK(h->red_part.alloc_zero((size_t)3 * h->nblk, st));
+  CK(h->red_gpart.alloc_zero((size_t)3 * cdiv(h->nblk, kRedGroup), st));
+  CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1, st));
+  CK(h->stage3.alloc_zero((size_t)N * 3, st));
   CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
-  CK(h->rank_scal.alloc_zero((size_t)h->world * 4));
+  CK(h->rank_scal.alloc_zero((size_t)h->world * 4, st));
   CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
   CKS(upload_poses(h, g->pose_xyt, h->xyt.p));
@@ -880,7 +905,7 @@ int dcs_get_hessian(dcs_handle* h, double* block_values) {
   std::vector<int32_t> flag((size_t)nh);
   if (nh > 0) {
     DevBuf<double> d_up;
-    CK(d_up.alloc_zero(up.size()));
+    CK(d_up.alloc_zero(up.size(), h->stream));
     LAUNCH(k_export_upper, cdiv(nh, 256), 256, h->stream, h->keys.p, h->up_scan.p, h->up_flag.p, h->slot.p, nh, h->Hoff.p, h->ldh, d_up.p);
     CK(cudaMemcpyAsync(up.data(), d_up.p, up.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -15,7 +15,8 @@ constexpr int kRowsPerBlock = 32;        // threads per CTA in the row-owner ker
 constexpr int kWindow = 1024;            // rows per jagged-diagonal window (sorted by degree inside it)
 constexpr int kSlice = 32;               // rows per warp task
 constexpr int kSlicesPerWindow = kWindow / kSlice;
-constexpr uint32_t kKeyNonOwner = 1u << 31;  // sort-key bit (col word): non-owner half-edges follow a row's owner ones
+constexpr uint32_t kKeyNonOwner = 1u << 27;  // sort-key bit just above the 27 column bits: non-owner half-edges follow a
+                                             // row's owner ones (the radix sort covers bits 0..27 of the column word)
 constexpr uint32_t kIdxMask = 0x07FFFFFFu;  // low 27 bits of a half-edge word: other pose (<= 134M poses)
 constexpr uint32_t kFlagSideB = 1u << 31;   // row pose is the edge's second endpoint (Edge::b)
 constexpr uint32_t kFlagDcs = 1u << 30;     // DCS functor applies (loop/bogus edge and METHOD 1)

@@ -205,6 +205,22 @@ __global__ void k_jds_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, con
   slot[i] = round_ptr[rp_off[w] + k] + rank_of[r];
 }
 
+// ---- odometry-chain entries for the segment preconditioner --------------------------------------------
+// chain_idx[r] = first (row,col)-sorted half-edge of local row r whose column is the next pose (r+1), or -1;
+// chain_cnt[r] = how many (duplicate edges between the same pair add up)
+__global__ void k_chain_entries(const uint64_t* keys, int32_t nh, int32_t row_lo, int32_t nrows, int32_t* chain_idx,
+                                int32_t* chain_cnt) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const uint64_t target = ((uint64_t)(uint32_t)(row_lo + r) << 32) | (uint32_t)(row_lo + r + 1);   // owner entry: bit 31 clear
+  int32_t lo = 0, hi = nh;
+  while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+  int32_t c = 0;
+  while (lo + c < nh && keys[lo + c] == target) ++c;
+  chain_idx[r] = c ? lo : -1;
+  chain_cnt[r] = c;
+}
+
 // ---- unique upper pattern (parity hook) ------------------------------------------------------------
 // flag[i] = 1 for the first sorted half-edge of every distinct (row,col) with row < col and col not
 // constant.  (Diagonal entries are added per non-empty row by the caller.)

@@ -37,6 +37,7 @@ class Options(C.Structure):
                 ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
                 ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
                 ("pcg_rel_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("pcg_check_every", C.c_int32),
+                ("preconditioner", C.c_int32),
                 ("device", C.c_int32), ("verbose", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("nccl_unique_id", C.c_void_p)]
 
