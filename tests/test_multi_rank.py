@@ -68,3 +68,14 @@ def test_two_gpu_ranks_match_single_rank():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "MGPU 2 ranks" in p.stdout
+
+
+@pytest.mark.gpu
+def test_four_gpu_ranks_match_single_rank():
+    if D.device_count() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "tests", "mgpu_worker.py"), "30000"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "MGPU 4 ranks" in p.stdout

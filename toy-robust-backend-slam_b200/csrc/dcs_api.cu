@@ -245,6 +245,10 @@ struct dcs_handle {
   DevBuf<float> chL, chS;                  // chain-segment preconditioner factors (fp32), step-major
   DevBuf<int32_t> chain_idx, chain_cnt;    // (r, r+1) entries in the sorted half-edge list
   int ntiles = 0;                          // 1024-pose tiles of the chain preconditioner
+  // halo exchange (world > 1): poses of other ranks my half-edges reference / my poses other ranks reference
+  DevBuf<int32_t> halo_send_idx, halo_recv_idx;
+  DevBuf<double4> halo_send_buf, halo_recv_buf;
+  std::vector<int32_t> halo_send_off, halo_recv_off;   // [world+1] offsets per peer
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
@@ -334,12 +338,82 @@ int allreduce_sum(dcs_handle* h, double* d, int count) {
   CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
   return DCS_OK;
 }
-// every rank owns rows [rank*rows_per_rank, ...) of a full-length array with `bytes_per_row`
+// every rank owns rows [rank*rows_per_rank, ...) of a full-length array with `bytes_per_row` (once per LM iteration:
+// the candidate poses, which the edge-sliced cost kernel reads at arbitrary endpoints)
 int allgather_rows(dcs_handle* h, void* full, size_t bytes_per_row) {
   if (h->world == 1) return DCS_OK;
   char* base = static_cast<char*>(full);
   const size_t chunk = (size_t)h->rows_per_rank * bytes_per_row;
   CKN(nccl_api().AllGather(base + (size_t)h->rank * chunk, base, chunk, ncclChar, h->comm, h->stream));
+  return DCS_OK;
+}
+
+// Halo exchange of a full-length double4 array whose owned slice [row_lo, row_lo + rows_per_rank) just changed:
+// every rank packs the owned entries its peers reference, grouped ncclSend/ncclRecv over NVLink move them, and the
+// received entries are scattered to their global positions.  Lists are static (built once from the pattern).
+int halo_exchange(dcs_handle* h, double4* arr) {
+  if (h->world == 1) return DCS_OK;
+  const int32_t ns = h->halo_send_off[h->world], nr = h->halo_recv_off[h->world];
+  if (ns > 0) LAUNCH(k_halo_pack, cdiv(ns, 256), 256, h->stream, arr, h->halo_send_idx.p, ns, h->halo_send_buf.p);
+  CKN(nccl_api().GroupStart());
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) continue;
+    const int32_t cs = h->halo_send_off[r + 1] - h->halo_send_off[r], cr = h->halo_recv_off[r + 1] - h->halo_recv_off[r];
+    if (cs > 0) CKN(nccl_api().Send(h->halo_send_buf.p + h->halo_send_off[r], (size_t)cs * 4, ncclDouble, r, h->comm, h->stream));
+    if (cr > 0) CKN(nccl_api().Recv(h->halo_recv_buf.p + h->halo_recv_off[r], (size_t)cr * 4, ncclDouble, r, h->comm, h->stream));
+  }
+  CKN(nccl_api().GroupEnd());
+  if (nr > 0) LAUNCH(k_halo_unpack, cdiv(nr, 256), 256, h->stream, h->halo_recv_buf.p, h->halo_recv_idx.p, nr, arr);
+  return DCS_OK;
+}
+
+// one-time: build the halo lists from the sorted half-edge keys and swap them with the peers
+int build_halo(dcs_handle* h, int32_t nh) {
+  const int W = h->world;
+  h->halo_send_off.assign(W + 1, 0);
+  h->halo_recv_off.assign(W + 1, 0);
+  if (W == 1) return DCS_OK;
+  cudaStream_t st = h->stream;
+  const int32_t NP = h->Npad;
+  DevBuf<int32_t> need, scan;
+  CK(need.alloc_zero((size_t)NP + 1, st));
+  CK(scan.alloc((size_t)NP + 1));
+  if (nh > 0) LAUNCH(k_halo_mark, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_lo + h->rows_per_rank, need.p);
+  CK(cudaMemcpyAsync(scan.p, need.p, ((size_t)NP + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  CKS(scan_exclusive(scan.p, (int64_t)NP + 1, st));
+  // receive offsets per owner rank = scan at the rank boundaries
+  std::vector<int32_t> bnd(W + 1);
+  for (int r = 0; r <= W; ++r) CK(cudaMemcpyAsync(&bnd[r], scan.p + (size_t)r * h->rows_per_rank, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int r = 0; r <= W; ++r) h->halo_recv_off[r] = bnd[r];
+  const int32_t nr = bnd[W];
+  CK(h->halo_recv_idx.alloc((size_t)std::max(nr, 1)));
+  LAUNCH(k_halo_compact, cdiv(NP, 256), 256, st, need.p, scan.p, NP, h->halo_recv_idx.p);
+  // counts: all-gather the per-owner receive counts of every rank, read column `rank` = what I must send to whom
+  DevBuf<int32_t> cnt_all;
+  CK(cnt_all.alloc((size_t)W * W));
+  std::vector<int32_t> my_cnt(W);
+  for (int r = 0; r < W; ++r) my_cnt[r] = bnd[r + 1] - bnd[r];
+  CK(cudaMemcpyAsync(cnt_all.p + (size_t)h->rank * W, my_cnt.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
+  CKN(nccl_api().AllGather(cnt_all.p + (size_t)h->rank * W, cnt_all.p, (size_t)W, ncclInt32, h->comm, st));
+  std::vector<int32_t> all((size_t)W * W);
+  CK(cudaMemcpyAsync(all.data(), cnt_all.p, all.size() * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int r = 0; r < W; ++r) h->halo_send_off[r + 1] = h->halo_send_off[r] + all[(size_t)r * W + h->rank];   // rank r needs that many of my rows
+  const int32_t ns = h->halo_send_off[W];
+  CK(h->halo_send_idx.alloc((size_t)std::max(ns, 1)));
+  // swap the index lists: I send each owner the (global) indices I need from it; I receive what each peer needs from me
+  CKN(nccl_api().GroupStart());
+  for (int r = 0; r < W; ++r) {
+    if (r == h->rank) continue;
+    const int32_t cr = h->halo_recv_off[r + 1] - h->halo_recv_off[r], cs = h->halo_send_off[r + 1] - h->halo_send_off[r];
+    if (cr > 0) CKN(nccl_api().Send(h->halo_recv_idx.p + h->halo_recv_off[r], (size_t)cr, ncclInt32, r, h->comm, st));
+    if (cs > 0) CKN(nccl_api().Recv(h->halo_send_idx.p + h->halo_send_off[r], (size_t)cs, ncclInt32, r, h->comm, st));
+  }
+  CKN(nccl_api().GroupEnd());
+  CK(h->halo_send_buf.alloc((size_t)std::max(ns, 1)));
+  CK(h->halo_recv_buf.alloc((size_t)std::max(nr, 1)));
+  CK(cudaStreamSynchronize(st));
   return DCS_OK;
 }
 
@@ -432,7 +506,7 @@ int pcg_iteration(dcs_handle* h, const double* D) {
   }
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
   LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->scal.p);
-  CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
+  CKS(halo_exchange(h, h->p4.p));
   return DCS_OK;
 }
 
@@ -455,7 +529,7 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
          h->z.p, h->p4.p, h->partials.p, h->tickets.p + 4, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
   LAUNCH(k_pcg_init_finish, 1, 1, h->stream, h->scal.p);
-  CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
+  CKS(halo_exchange(h, h->p4.p));
   CKS(read_scalars(h));
   const double rr0 = h->h_scal[S_RR0];
   int iters = 0;
@@ -603,6 +677,8 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   if (o->device < 0 || o->device >= ndev) { g_err = "dcs_create: no such CUDA device"; return DCS_ERR_CUDA; }
   CK(cudaSetDevice(o->device));
 
+  const double t_c0 = now_s();
+  auto lap = [&](const char* what) { if (std::getenv("DCS_CREATE_TIMING")) { cudaDeviceSynchronize(); std::fprintf(stderr, "[dcs_create] %-28s %.3f s\n", what, now_s() - t_c0); } };
   dcs_handle* h = new dcs_handle();
   struct Guard { dcs_handle* h; ~Guard() { if (h) dcs_destroy(h); } } guard{h};
   h->opt = *o;
@@ -637,6 +713,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   h->ldn = (int64_t)h->nwin * kWindow;
   h->e_lo = part[3]; h->e_hi = part[4];
 
+  lap("stream/nccl");
   // ---- upload the graph ---------------------------------------------------------------------
   DevBuf<double> d_meas;
   DevBuf<uint8_t> d_kind;
@@ -654,6 +731,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   if (E > 0) LAUNCH(k_edge_prep, cdiv(E, 256), 256, st, d_meas.p, d_kind.p, E, o->dcs_on, h->e_tmx.p, h->e_tmy.p, h->e_thm.p,
                     h->e_dcs.p);
 
+  lap("upload + edge prep");
   // ---- K0: half-edges, sort, CSR, jagged-diagonal re-layout ---------------------------------------
   CK(h->deg_all.alloc_zero((size_t)h->Npad, st));
   if (E > 0) LAUNCH(k_pose_degree, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->deg_all.p);
@@ -676,6 +754,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const int nb = bits_for(std::max(N, 2));
   CKS(radix_sort(h->keys, h->vals, nh, 28, nb, st));   // column word: 27 index bits + the owner-order bit
 
+  lap("half-edges + radix sort");
   CK(h->row_ptr.alloc((size_t)h->ldn + 1));
   {
     // rows beyond nrows (padding) get the end offset so their degree is zero
@@ -709,6 +788,8 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     CK(cudaStreamSynchronize(st));
   }
 
+  CKS(build_halo(h, nh));
+  lap("jds layout + fill");
   // unique upper pattern (parity hook)
   CK(h->up_flag.alloc_zero((size_t)nh + 1, st)); CK(h->up_scan.alloc_zero((size_t)nh + 1, st));
   if (nh > 0) {
@@ -719,6 +800,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     CK(cudaStreamSynchronize(st));
   }
 
+  lap("upper pattern");
   // ---- state --------------------------------------------------------------------------------------
   const size_t NP = (size_t)h->Npad, LN = (size_t)h->ldn;
   CK(h->xyt.alloc_zero(NP, st)); CK(h->cand_xyt.alloc_zero(NP, st)); CK(h->p4.alloc_zero(NP, st));
@@ -743,9 +825,11 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->rank_scal.alloc_zero((size_t)h->world * 4, st));
   CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
+  lap("state alloc");
   CKS(upload_poses(h, g->pose_xyt, h->xyt.p));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  lap("pose upload");
   guard.h = nullptr;
   *out = h;
   return DCS_OK;
@@ -1055,7 +1139,7 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, h->grad.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->partials.p,
            h->tickets.p + 4, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
-    CKS(allgather_rows(h, h->p4.p, sizeof(double4)));
+    CKS(halo_exchange(h, h->p4.p));
     CKS(ensure_mirror(h));
     LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->task_part.p);
     k_fold_tasks<1, 0><<<1, kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + S_WHW, h->scal.p, 0);

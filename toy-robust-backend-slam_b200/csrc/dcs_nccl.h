@@ -16,6 +16,10 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 
   bool load() {
@@ -29,6 +33,10 @@ struct NcclApi {
     DCS_NCCL_SYM(CommDestroy, "ncclCommDestroy");
     DCS_NCCL_SYM(AllReduce, "ncclAllReduce");
     DCS_NCCL_SYM(AllGather, "ncclAllGather");
+    DCS_NCCL_SYM(Send, "ncclSend");
+    DCS_NCCL_SYM(Recv, "ncclRecv");
+    DCS_NCCL_SYM(GroupStart, "ncclGroupStart");
+    DCS_NCCL_SYM(GroupEnd, "ncclGroupEnd");
     DCS_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef DCS_NCCL_SYM
     return true;

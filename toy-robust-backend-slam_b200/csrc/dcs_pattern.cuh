@@ -221,6 +221,27 @@ __global__ void k_chain_entries(const uint64_t* keys, int32_t nh, int32_t row_lo
   chain_cnt[r] = c;
 }
 
+// ---- halo lists (multi-rank): which poses of other ranks do my half-edges reference -----------------------
+__global__ void k_halo_mark(const uint64_t* keys, int32_t nh, int32_t row_lo, int32_t row_hi, int32_t* need) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int32_t col = (int32_t)(keys[i] & kIdxMask);
+  if (col < row_lo || col >= row_hi) need[col] = 1;      // benign race: everybody writes 1
+}
+// compaction: list[scan[j]] = j for every marked pose (scan = exclusive scan of need)
+__global__ void k_halo_compact(const int32_t* need, const int32_t* scan, int32_t n, int32_t* list) {
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n && need[j]) list[scan[j]] = j;
+}
+__global__ void k_halo_pack(const double4* __restrict__ arr, const int32_t* __restrict__ idx, int32_t n, double4* buf) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = arr[idx[i]];
+}
+__global__ void k_halo_unpack(const double4* __restrict__ buf, const int32_t* __restrict__ idx, int32_t n, double4* arr) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) arr[idx[i]] = buf[i];
+}
+
 // ---- unique upper pattern (parity hook) ------------------------------------------------------------
 // flag[i] = 1 for the first sorted half-edge of every distinct (row,col) with row < col and col not
 // constant.  (Diagonal entries are added per non-empty row by the caller.)
