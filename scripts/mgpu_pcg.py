@@ -23,6 +23,12 @@ x, sm, tr = s.solve()
 if rank == 0:
     print(f"world {world}: N={N} E={g.n_edges} linearize {us:.1f} us/step, pcg {1e6 * sm.linear_solver_time_s / max(1, sm.total_pcg_iterations):.1f} us/iter "
           f"({sm.total_pcg_iterations} iterations)", flush=True)
+import ctypes as C
+lib = D.load_library(); out = (C.c_double * 4)()
+lib.dcs_debug_comm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.dcs_debug_comm(s.h, 50, out)
+if rank == 0:
+    print(f"world {world}: halo exchange {out[0]:.1f} us ({out[3]:.1f} MB sent per rank), allreduce(1) {out[1]:.1f} us, allreduce(2) {out[2]:.1f} us", flush=True)
 s.close()
 dist.barrier()
 dist.destroy_process_group()

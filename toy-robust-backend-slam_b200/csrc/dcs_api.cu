@@ -100,7 +100,7 @@ __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32
                                  int32_t nh, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                  const int32_t* __restrict__ deg_all, int32_t fixed, const double* __restrict__ tmx,
                                  const double* __restrict__ tmy, const double* __restrict__ thm,
-                                 const uint8_t* __restrict__ dcs_flag, int32_t row_lo, int32_t row_hi,
+                                 const uint8_t* __restrict__ dcs_flag, int32_t row_lo, int32_t row_hi, const int32_t* __restrict__ g2l,
                                  uint32_t* h_other, double* h_tmx, double* h_tmy, double* h_thm, int32_t* edge_slot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
@@ -110,7 +110,7 @@ __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32
   const int32_t other = (int32_t)(keys[i] & kIdxMask);
   const int32_t row = (int32_t)(keys[i] >> 32);
   const int32_t a = ea[e];
-  uint32_t word = (uint32_t)other;
+  uint32_t word = (uint32_t)g2l[other];      // gathered arrays are indexed locally: [own rows | halo]
   if (side_b) word |= kFlagSideB;
   if (dcs_flag[e]) word |= kFlagDcs;
   if (other == fixed) word |= kFlagOtherFixed;
@@ -139,6 +139,11 @@ __global__ void k_mirror_src(const uint32_t* __restrict__ vals, const int32_t* _
     src = edge_slot[2 * (int64_t)(v >> 1) + ((v & 1u) ^ 1u)];
   }
   mirror_src[s] = src;
+}
+
+__global__ void k_global_to_own(int32_t* idx, int32_t n, int32_t row_lo) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] -= row_lo;
 }
 
 __global__ void k_is_free(const int32_t* __restrict__ deg_all, int32_t row_lo, int32_t nrows, int32_t fixed, uint8_t* is_free) {
@@ -246,8 +251,9 @@ struct dcs_handle {
   DevBuf<int32_t> chain_idx, chain_cnt;    // (r, r+1) entries in the sorted half-edge list
   int ntiles = 0;                          // 1024-pose tiles of the chain preconditioner
   // halo exchange (world > 1): poses of other ranks my half-edges reference / my poses other ranks reference
-  DevBuf<int32_t> halo_send_idx, halo_recv_idx;
-  DevBuf<double4> halo_send_buf, halo_recv_buf;
+  DevBuf<int32_t> halo_send_idx, halo_recv_idx, g2l;   // send: LOCAL own-row indices; recv: GLOBAL indices; g2l: global -> local
+  DevBuf<double4> halo_send_buf;
+  int32_t n_halo = 0, n_loc = 0;                       // local index space = [rows_per_rank own | n_halo halo]
   std::vector<int32_t> halo_send_off, halo_recv_off;   // [world+1] offsets per peer
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
@@ -261,7 +267,7 @@ struct dcs_handle {
 
   RowLayout layout() const {
     RowLayout L;
-    L.row_lo = row_lo; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;
+    L.row_lo = 0; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;   // gathered arrays are indexed locally: own rows start at 0
     L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
     L.nwin = nwin; L.ntasks = ntasks;
     return L;
@@ -338,32 +344,21 @@ int allreduce_sum(dcs_handle* h, double* d, int count) {
   CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
   return DCS_OK;
 }
-// every rank owns rows [rank*rows_per_rank, ...) of a full-length array with `bytes_per_row` (once per LM iteration:
-// the candidate poses, which the edge-sliced cost kernel reads at arbitrary endpoints)
-int allgather_rows(dcs_handle* h, void* full, size_t bytes_per_row) {
-  if (h->world == 1) return DCS_OK;
-  char* base = static_cast<char*>(full);
-  const size_t chunk = (size_t)h->rows_per_rank * bytes_per_row;
-  CKN(nccl_api().AllGather(base + (size_t)h->rank * chunk, base, chunk, ncclChar, h->comm, h->stream));
-  return DCS_OK;
-}
-
-// Halo exchange of a full-length double4 array whose owned slice [row_lo, row_lo + rows_per_rank) just changed:
-// every rank packs the owned entries its peers reference, grouped ncclSend/ncclRecv over NVLink move them, and the
-// received entries are scattered to their global positions.  Lists are static (built once from the pattern).
+// Halo exchange of a locally indexed double4 array ([own rows | halo]) whose own rows just changed: every rank packs
+// the own entries its peers reference; grouped ncclSend/ncclRecv over NVLink move them straight into the peers' halo
+// regions (the halo is stored in global order, i.e. grouped by owner, so no unpack pass is needed).
 int halo_exchange(dcs_handle* h, double4* arr) {
   if (h->world == 1) return DCS_OK;
-  const int32_t ns = h->halo_send_off[h->world], nr = h->halo_recv_off[h->world];
+  const int32_t ns = h->halo_send_off[h->world];
   if (ns > 0) LAUNCH(k_halo_pack, cdiv(ns, 256), 256, h->stream, arr, h->halo_send_idx.p, ns, h->halo_send_buf.p);
   CKN(nccl_api().GroupStart());
   for (int r = 0; r < h->world; ++r) {
     if (r == h->rank) continue;
     const int32_t cs = h->halo_send_off[r + 1] - h->halo_send_off[r], cr = h->halo_recv_off[r + 1] - h->halo_recv_off[r];
     if (cs > 0) CKN(nccl_api().Send(h->halo_send_buf.p + h->halo_send_off[r], (size_t)cs * 4, ncclDouble, r, h->comm, h->stream));
-    if (cr > 0) CKN(nccl_api().Recv(h->halo_recv_buf.p + h->halo_recv_off[r], (size_t)cr * 4, ncclDouble, r, h->comm, h->stream));
+    if (cr > 0) CKN(nccl_api().Recv(arr + h->rows_per_rank + h->halo_recv_off[r], (size_t)cr * 4, ncclDouble, r, h->comm, h->stream));
   }
   CKN(nccl_api().GroupEnd());
-  if (nr > 0) LAUNCH(k_halo_unpack, cdiv(nr, 256), 256, h->stream, h->halo_recv_buf.p, h->halo_recv_idx.p, nr, arr);
   return DCS_OK;
 }
 
@@ -372,9 +367,9 @@ int build_halo(dcs_handle* h, int32_t nh) {
   const int W = h->world;
   h->halo_send_off.assign(W + 1, 0);
   h->halo_recv_off.assign(W + 1, 0);
-  if (W == 1) return DCS_OK;
   cudaStream_t st = h->stream;
   const int32_t NP = h->Npad;
+  CK(h->g2l.alloc((size_t)NP));
   DevBuf<int32_t> need, scan;
   CK(need.alloc_zero((size_t)NP + 1, st));
   CK(scan.alloc((size_t)NP + 1));
@@ -387,8 +382,11 @@ int build_halo(dcs_handle* h, int32_t nh) {
   CK(cudaStreamSynchronize(st));
   for (int r = 0; r <= W; ++r) h->halo_recv_off[r] = bnd[r];
   const int32_t nr = bnd[W];
+  h->n_halo = nr;
+  h->n_loc = h->rows_per_rank + nr;
   CK(h->halo_recv_idx.alloc((size_t)std::max(nr, 1)));
-  LAUNCH(k_halo_compact, cdiv(NP, 256), 256, st, need.p, scan.p, NP, h->halo_recv_idx.p);
+  LAUNCH(k_halo_compact, cdiv(NP, 256), 256, st, need.p, scan.p, NP, h->row_lo, h->rows_per_rank, h->halo_recv_idx.p, h->g2l.p);
+  if (W == 1) { CK(cudaStreamSynchronize(st)); return DCS_OK; }
   // counts: all-gather the per-owner receive counts of every rank, read column `rank` = what I must send to whom
   DevBuf<int32_t> cnt_all;
   CK(cnt_all.alloc((size_t)W * W));
@@ -412,7 +410,7 @@ int build_halo(dcs_handle* h, int32_t nh) {
   }
   CKN(nccl_api().GroupEnd());
   CK(h->halo_send_buf.alloc((size_t)std::max(ns, 1)));
-  CK(h->halo_recv_buf.alloc((size_t)std::max(nr, 1)));
+  if (ns > 0) LAUNCH(k_global_to_own, cdiv(ns, 256), 256, st, h->halo_send_idx.p, ns, h->row_lo);   // peers asked with global ids
   CK(cudaStreamSynchronize(st));
   return DCS_OK;
 }
@@ -438,7 +436,7 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// host N x 3 poses -> device packed poses
+// host N x 3 poses -> device packed poses (own rows + halo, local order)
 int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt) {
   const double* src = pose_xyt;
   if (!is_pinned(pose_xyt)) {       // pageable caller memory: bounce through the handle's pinned buffer
@@ -446,11 +444,18 @@ int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt) {
     src = h->h_pin3;
   }
   CK(cudaMemcpyAsync(h->stage3.p, src, (size_t)h->N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(k_pack_poses, cdiv(h->N, 256), 256, h->stream, h->stage3.p, h->N, xyt);
+  LAUNCH(k_pack_poses, cdiv(h->n_loc, 256), 256, h->stream, h->stage3.p, h->N, h->row_lo, h->rows_per_rank, h->halo_recv_idx.p,
+         h->n_loc, xyt);
   return DCS_OK;
 }
+// own rows of every rank -> host N x 3
 int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
-  LAUNCH(k_unpack_poses, cdiv(h->N, 256), 256, h->stream, xyt, h->N, h->stage3.p);
+  LAUNCH(k_unpack_poses, cdiv(h->rows_per_rank, 256), 256, h->stream, xyt, h->row_lo, h->rows_per_rank, h->N, h->stage3.p);
+  if (h->world > 1) {     // stage3 is Npad x 3: equal slices, in-place all-gather
+    char* base = reinterpret_cast<char*>(h->stage3.p);
+    const size_t chunk = (size_t)h->rows_per_rank * 24;
+    CKN(nccl_api().AllGather(base + (size_t)h->rank * chunk, base, chunk, ncclChar, h->comm, h->stream));
+  }
   CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   std::memcpy(pose_xyt, h->h_pin3, (size_t)h->N * 3 * sizeof(double));
@@ -481,10 +486,9 @@ int ensure_mirror(dcs_handle* h) {
 }
 
 int cost_only(dcs_handle* h, const double4* xyt, int slot) {
-  const int ne = h->e_hi - h->e_lo;
-  const int grid = std::max(1, std::min(cdiv(ne, kEdgeThreads), 148 * 8));
-  LAUNCH(k_cost, grid, kEdgeThreads, h->stream, xyt, h->edgelist(), h->e_lo, h->e_hi, h->P, h->partials.p, h->tickets.p + 2,
-         h->scal.p + slot);
+  LAUNCH(k_cost_rows, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->task_part.p);
+  k_fold_tasks<1, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + slot, h->scal.p, 0);
+  ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + slot, 1));
   return DCS_OK;
 }
@@ -497,15 +501,15 @@ int pcg_iteration(dcs_handle* h, const double* D) {
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
-           h->row_lo, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+           0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0);
     ++g_launches;
   } else {
-    LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, h->row_lo, h->nrows, h->ldn, h->w.p,
+    LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, 0, h->nrows, h->ldn, h->w.p,
            h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
   }
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
-  LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->scal.p);
+  LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, 0, h->nrows, h->ldn, h->p4.p, h->scal.p);
   CKS(halo_exchange(h, h->p4.p));
   return DCS_OK;
 }
@@ -520,12 +524,12 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_chain_factor, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->nrows, h->ldn,
            h->ldh, h->chL.p, h->chS.p);
-    LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->row_lo, h->nrows,
+    LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, 0, h->nrows,
            h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0);
     ++g_launches;
   } else
-  LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->w.p, h->r.p,
+  LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, 0, h->nrows, h->ldn, h->w.p, h->r.p,
          h->z.p, h->p4.p, h->partials.p, h->tickets.p + 4, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
   LAUNCH(k_pcg_init_finish, 1, 1, h->stream, h->scal.p);
@@ -774,6 +778,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   if (nh > 0) LAUNCH(k_jds_slot, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_ptr.p, h->rank_of.p, h->rp_off.p,
                      h->round_ptr.p, h->slot.p);
 
+  CKS(build_halo(h, nh));      // halo lists + the global -> local index map the half-edge words use
   const size_t HH = (size_t)h->ldh;
   CK(h->h_other.alloc_zero(HH, st)); CK(h->h_tmx.alloc_zero(HH, st)); CK(h->h_tmy.alloc_zero(HH, st)); CK(h->h_thm.alloc_zero(HH, st));
   CK(h->mirror_src.alloc((size_t)std::max(nh, 1)));
@@ -782,13 +787,12 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     CK(edge_slot.alloc((size_t)2 * EE));
     CK(cudaMemsetAsync(edge_slot.p, 0xFF, (size_t)2 * EE * 4, st));
     LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
-           h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->h_other.p,
+           h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->g2l.p, h->h_other.p,
            h->h_tmx.p, h->h_tmy.p, h->h_thm.p, edge_slot.p);
     LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, h->mirror_src.p);
     CK(cudaStreamSynchronize(st));
   }
 
-  CKS(build_halo(h, nh));
   lap("jds layout + fill");
   // unique upper pattern (parity hook)
   CK(h->up_flag.alloc_zero((size_t)nh + 1, st)); CK(h->up_scan.alloc_zero((size_t)nh + 1, st));
@@ -802,8 +806,9 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
 
   lap("upper pattern");
   // ---- state --------------------------------------------------------------------------------------
-  const size_t NP = (size_t)h->Npad, LN = (size_t)h->ldn;
-  CK(h->xyt.alloc_zero(NP, st)); CK(h->cand_xyt.alloc_zero(NP, st)); CK(h->p4.alloc_zero(NP, st));
+  const size_t LN = (size_t)h->ldn;
+  const size_t NL = (size_t)std::max(h->n_loc, 1);
+  CK(h->xyt.alloc_zero(NL, st)); CK(h->cand_xyt.alloc_zero(NL, st)); CK(h->p4.alloc_zero(NL, st));
   CK(h->Hoff.alloc_zero(9 * HH, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
   CK(h->scale.alloc_zero(3 * LN, st)); CK(h->lmdiag.alloc_zero(3 * LN, st)); CK(h->Adiag.alloc_zero(6 * LN, st)); CK(h->Minv.alloc_zero(6 * LN, st));
   CK(h->w.alloc_zero(3 * LN, st)); CK(h->r.alloc_zero(3 * LN, st)); CK(h->q.alloc_zero(3 * LN, st)); CK(h->z.alloc_zero(3 * LN, st));
@@ -820,7 +825,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->red_part.alloc_zero((size_t)3 * h->nblk, st));
   CK(h->red_gpart.alloc_zero((size_t)3 * cdiv(h->nblk, kRedGroup), st));
   CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1, st));
-  CK(h->stage3.alloc_zero((size_t)N * 3, st));
+  CK(h->stage3.alloc_zero((size_t)h->Npad * 3, st));
   CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
   CK(h->rank_scal.alloc_zero((size_t)h->world * 4, st));
   CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
@@ -844,6 +849,10 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
   CKS(read_scalars(h));
   if (cost) *cost = h->h_scal[S_COST];
   const int32_t E = h->E;
+  if ((residuals || jacobians || psi || rho1) && h->world > 1) {
+    g_err = "dcs_evaluate: per-edge outputs are available on single-rank handles only";
+    return DCS_ERR_ARG;
+  }
   if ((residuals || jacobians || psi || rho1) && E > 0) {
     DevBuf<double> dr, dj, dp, dq;
     if (residuals) CK(dr.alloc((size_t)E * 3));
@@ -930,6 +939,25 @@ extern "C" double dcs_debug_atomic(dcs_handle* h, int nper, int repeats) {
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   cudaFree(acc);
   return 1e3 * ms / repeats;
+}
+
+// development probe: time the exchange steps of one PCG iteration (us each, averaged over `repeats`)
+extern "C" int dcs_debug_comm(dcs_handle* h, int repeats, double* out4) {
+  cudaSetDevice(h->dev);
+  auto timeit = [&](auto&& fn) -> double {
+    for (int i = 0; i < 3; ++i) fn();
+    cudaEventRecord(h->ev0, h->stream);
+    for (int i = 0; i < repeats; ++i) fn();
+    cudaEventRecord(h->ev1, h->stream);
+    cudaEventSynchronize(h->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    return 1e3 * ms / repeats;
+  };
+  out4[0] = timeit([&] { halo_exchange(h, h->p4.p); });
+  out4[1] = timeit([&] { allreduce_sum(h, h->scal.p + S_PQ, 1); });
+  out4[2] = timeit([&] { allreduce_sum(h, h->scal.p + S_TMP, 2); });
+  out4[3] = (double)h->halo_send_off[h->world] * 32.0 / 1e6;   // MB sent per exchange
+  return DCS_OK;
 }
 
 int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost) {
@@ -1070,7 +1098,7 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
   };
 
   CKS(upload_poses(h, pose_xyt_inout, h->xyt.p));
-  LAUNCH(k_xnorm, h->vec_grid(), kVecThreads, st, h->xyt.p, h->is_free.p, h->row_lo, h->nrows, h->partials.p, h->tickets.p + 5, h->scal.p);
+  LAUNCH(k_xnorm, h->vec_grid(), kVecThreads, st, h->xyt.p, h->is_free.p, 0, h->nrows, h->partials.p, h->tickets.p + 5, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_XSQ, 1));
   CKS(timed_linearize(h->xyt.p));
   double x_cost = h->h_scal[S_COST];
@@ -1136,7 +1164,7 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     it.linear_solver_residual = pcg_rel;
 
     // model_cost_change = w.g - w.H.w / 2
-    LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, h->grad.p, h->row_lo, h->nrows, h->ldn, h->p4.p, h->partials.p,
+    LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, h->grad.p, 0, h->nrows, h->ldn, h->p4.p, h->partials.p,
            h->tickets.p + 4, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
     CKS(halo_exchange(h, h->p4.p));
@@ -1146,10 +1174,10 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     ++g_launches;
     CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
     // candidate = x - w
-    LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, h->row_lo, h->nrows, h->ldn, h->cand_xyt.p,
+    LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, 0, h->nrows, h->ldn, h->cand_xyt.p,
            h->partials.p, h->tickets.p + 5, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_STEP_SQ, 2));
-    CKS(allgather_rows(h, h->cand_xyt.p, sizeof(double4)));
+    CKS(halo_exchange(h, h->cand_xyt.p));
     CK(cudaEventRecord(h->ev0, st));
     CKS(cost_only(h, h->cand_xyt.p, S_CAND_COST));
     CK(cudaEventRecord(h->ev1, st));

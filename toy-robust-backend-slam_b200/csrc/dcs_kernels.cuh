@@ -235,6 +235,37 @@ struct EdgeList {
 
 constexpr int kEdgeThreads = 256;
 
+// K6: cost at a candidate point over the rank's own rows: every edge is booked on exactly one half-edge
+// (kFlagCost), so each rank needs only its own + halo poses and the ranks' partial costs add up.
+__global__ void __launch_bounds__(kRowsPerBlock)
+k_cost_rows(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P, double* __restrict__ task_part) {
+  const L2Policy pol = make_l2_policy();
+  const WarpTask wt = warp_task(L);
+  const int t = wt.rank;
+  const int lr = wt.lr;
+  double cost = 0.0;
+  if (wt.valid && lr < L.nrows) {
+    const int deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
+    const double4 po = ld_keep4(xyt + L.row_lo + lr, pol.keep);
+    for (int k = 0; k < deg; ++k) {
+      const int64_t idx = (int64_t)wt.rp[k] + t;
+      const uint32_t word = ld_stream_u32(H.other + idx, pol.stream);
+      if (!(word & kFlagCost)) continue;
+      const double4 pj = ld_keep4(xyt + (word & kIdxMask), pol.keep);
+      const bool side_b = (word & kFlagSideB) != 0;
+      const double xa = side_b ? pj.x : po.x, ya = side_b ? pj.y : po.y, tha = side_b ? pj.z : po.z;
+      const double xb = side_b ? po.x : pj.x, yb = side_b ? po.y : pj.y, thb = side_b ? po.z : pj.z;
+      double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
+      cost += edge_cost_terms(xa, ya, tha, xb, yb, thb, ld_stream(H.tmx + idx, pol.stream), ld_stream(H.tmy + idx, pol.stream),
+                              ld_stream(H.thm + idx, pol.stream), (word & kFlagDcs) != 0, P, q00, q01, dxw, dyw, epx, epy, ex, ey,
+                              eth, sigma, psi2, inv_den, e2, rho1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+  if ((threadIdx.x & 31) == 0) task_part[blockIdx.x] = cost;
+}
+
 __global__ void __launch_bounds__(kEdgeThreads)
 k_cost(const double4* __restrict__ xyt, EdgeList E, int32_t e_lo, int32_t e_hi, Params P,
        double* partials, unsigned int* ticket, double* out) {
@@ -275,16 +306,23 @@ k_edge_eval(const double4* __restrict__ xyt, EdgeList E, Params P, double* res, 
 // ------------------------------------------------------------------------------------------------
 // pose upload helpers
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_poses(const double* __restrict__ xyt3, int32_t n, double4* xyt) {
+// Device poses live in the rank's LOCAL index space: [own rows | halo poses in global order].  32-byte records: one
+// sector per gather; the whole gathered working set (own + halo) is contiguous and stays L2 resident.
+__global__ void k_pack_poses(const double* __restrict__ xyt3, int32_t n_global, int32_t row_lo, int32_t rows_per_rank,
+                             const int32_t* __restrict__ halo_idx, int32_t n_loc, double4* xyt) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  xyt[i] = make_double4(xyt3[3 * i], xyt3[3 * i + 1], xyt3[3 * i + 2], 0.0);   // 32-byte records: one sector per gather
+  if (i >= n_loc) return;
+  const int32_t j = i < rows_per_rank ? row_lo + i : halo_idx[i - rows_per_rank];
+  xyt[i] = j < n_global ? make_double4(xyt3[3 * (int64_t)j], xyt3[3 * (int64_t)j + 1], xyt3[3 * (int64_t)j + 2], 0.0)
+                        : make_double4(0, 0, 0, 0);
 }
-__global__ void k_unpack_poses(const double4* __restrict__ xyt, int32_t n, double* xyt3) {
+// own rows -> global N x 3 staging
+__global__ void k_unpack_poses(const double4* __restrict__ xyt, int32_t row_lo, int32_t rows, int32_t n_global, double* xyt3) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= rows || row_lo + i >= n_global) return;
   const double4 p = xyt[i];
-  xyt3[3 * i] = p.x; xyt3[3 * i + 1] = p.y; xyt3[3 * i + 2] = p.z;
+  const int64_t j = row_lo + i;
+  xyt3[3 * j] = p.x; xyt3[3 * j + 1] = p.y; xyt3[3 * j + 2] = p.z;
 }
 
 // ------------------------------------------------------------------------------------------------

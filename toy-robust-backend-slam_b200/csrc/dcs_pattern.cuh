@@ -228,18 +228,20 @@ __global__ void k_halo_mark(const uint64_t* keys, int32_t nh, int32_t row_lo, in
   const int32_t col = (int32_t)(keys[i] & kIdxMask);
   if (col < row_lo || col >= row_hi) need[col] = 1;      // benign race: everybody writes 1
 }
-// compaction: list[scan[j]] = j for every marked pose (scan = exclusive scan of need)
-__global__ void k_halo_compact(const int32_t* need, const int32_t* scan, int32_t n, int32_t* list) {
+// compaction: list[scan[j]] = j for every marked pose (scan = exclusive scan of need), and the global -> local
+// index map of the rank: own rows first ([0, rows_per_rank)), then the halo in global order
+__global__ void k_halo_compact(const int32_t* need, const int32_t* scan, int32_t n, int32_t row_lo, int32_t rows_per_rank,
+                               int32_t* list, int32_t* g2l) {
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n && need[j]) list[scan[j]] = j;
+  if (j >= n) return;
+  int32_t l = -1;
+  if (j >= row_lo && j < row_lo + rows_per_rank) l = j - row_lo;
+  else if (need[j]) { list[scan[j]] = j; l = rows_per_rank + scan[j]; }
+  g2l[j] = l;
 }
 __global__ void k_halo_pack(const double4* __restrict__ arr, const int32_t* __restrict__ idx, int32_t n, double4* buf) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) buf[i] = arr[idx[i]];
-}
-__global__ void k_halo_unpack(const double4* __restrict__ buf, const int32_t* __restrict__ idx, int32_t n, double4* arr) {
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) arr[idx[i]] = buf[i];
 }
 
 // ---- unique upper pattern (parity hook) ------------------------------------------------------------
