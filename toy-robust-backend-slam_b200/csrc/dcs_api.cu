@@ -246,6 +246,7 @@ struct dcs_handle {
   double lin_cost = 0, lin_gsq = 0, lin_gmax = 0;
   bool lin_scal_pending = false;           // per-rank scalars not folded into h_scal yet
   DevBuf<unsigned int> red_tickets;        // [ngroups] group tickets + [1] global ticket
+  DevBuf<double> fold_ws;                  // k_fold_tasks per-CTA partials [(K+M) <= 4][32]
   DevBuf<double> task_part;                // [3][ntasks] per-task partial sums of the row-owner kernels
   DevBuf<float> chL, chS;                  // chain-segment preconditioner factors (fp32), step-major
   DevBuf<int32_t> chain_idx, chain_cnt;    // (r, r+1) entries in the sorted half-edge list
@@ -466,7 +467,7 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 int linearize(dcs_handle* h, const double4* xyt) {
   LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
          h->grad.p, h->task_part.p);
-  k_fold_tasks<2, 1><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0);
+  k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
   if (h->world > 1) {   // one collective: every rank's (cost, |g|^2, |g|_inf); folded on the host in rank order
     CKN(nccl_api().AllGather(h->scal.p + S_COST, h->rank_scal.p, 4, ncclDouble, h->comm, h->stream));
@@ -487,7 +488,7 @@ int ensure_mirror(dcs_handle* h) {
 
 int cost_only(dcs_handle* h, const double4* xyt, int slot) {
   LAUNCH(k_cost_rows, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->task_part.p);
-  k_fold_tasks<1, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + slot, h->scal.p, 0);
+  k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + slot, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + slot, 1));
   return DCS_OK;
@@ -496,13 +497,13 @@ int cost_only(dcs_handle* h, const double4* xyt, int slot) {
 // one PCG iteration on the stream (capturable)
 int pcg_iteration(dcs_handle* h, const double* D) {
   LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->task_part.p);
-  k_fold_tasks<1, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1);
+  k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
            0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
-    k_fold_tasks<2, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0);
+    k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches;
   } else {
     LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, 0, h->nrows, h->ldn, h->w.p,
@@ -526,7 +527,7 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
            h->ldh, h->chL.p, h->chS.p);
     LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, 0, h->nrows,
            h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
-    k_fold_tasks<2, 0><<<1, kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0);
+    k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches;
   } else
   LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, 0, h->nrows, h->ldn, h->w.p, h->r.p,
@@ -767,7 +768,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   }
   CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
   CK(h->rp_off.alloc_zero((size_t)h->nwin + 1, st));
-  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
+  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
   CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nwin + 1, st));
   int32_t n_rounds = 0;
   CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nwin, 4, cudaMemcpyDeviceToHost, st));
@@ -817,6 +818,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->partials.alloc_zero(4 * max_grid, st));
   CK(h->scal.alloc_zero(S_COUNT, st));
   CK(h->tickets.alloc_zero(8, st));
+  CK(h->fold_ws.alloc_zero(4 * kFoldMaxBlocks, st));
   h->ntiles = (int)(h->ldn / kChainTile);
   CK(h->chL.alloc_zero(9 * LN, st)); CK(h->chS.alloc_zero(6 * LN, st));
   CK(h->chain_idx.alloc_zero(LN, st)); CK(h->chain_cnt.alloc_zero(LN, st));
@@ -1170,7 +1172,7 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     CKS(halo_exchange(h, h->p4.p));
     CKS(ensure_mirror(h));
     LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->task_part.p);
-    k_fold_tasks<1, 0><<<1, kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + S_WHW, h->scal.p, 0);
+    k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + S_WHW, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches;
     CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
     // candidate = x - w

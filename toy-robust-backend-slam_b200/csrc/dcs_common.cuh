@@ -279,6 +279,22 @@ __device__ __forceinline__ double4 ld_keep4(const double4* p, uint64_t pol) {
   asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2+16], %3;" : "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
   return v;
 }
+// Predicated forms (one @p instruction each, no branch around the load: a branch would make ptxas re-arm the
+// consumer's scoreboard wait on the path that skipped it).  The destination keeps its value when `on` is false.
+__device__ __forceinline__ void ld_stream_if(double& v, const double* p, uint64_t pol, bool on) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;\n\t}"
+               : "+d"(v) : "l"(p), "l"(pol), "r"((int)on));
+}
+__device__ __forceinline__ void ld_stream_u32_if(uint32_t& v, const uint32_t* p, uint64_t pol, bool on) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;\n\t}"
+               : "+r"(v) : "l"(p), "l"(pol), "r"((int)on));
+}
+__device__ __forceinline__ void ld_keep3_if(double& x, double& y, double& z, const double4* p, uint64_t pol, bool on) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%3], %4;\n\t"
+               "@q ld.global.nc.L2::cache_hint.f64 %2, [%3+16], %4;\n\t}"
+               : "+d"(x), "+d"(y), "+d"(z) : "l"(p), "l"(pol), "r"((int)on));
+}
 __device__ __forceinline__ double2 ld_keep2(const double2* p, uint64_t pol) {
   double2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));

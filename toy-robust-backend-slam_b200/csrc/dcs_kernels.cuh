@@ -128,24 +128,41 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     }
   };
 
-  // software pipeline, unrolled by two so buffers alternate instead of being copied: words run two
-  // rounds ahead, the measurement record and the gathered pose one round ahead
-  uint32_t w0 = 0, w1 = 0;
-  HalfEdgeRec recA, recB;
-  PoseRec poseA, poseB;
-  if (deg > 0) w0 = ld_stream_u32(H.other + rp[0] + t, pol.stream);
-  if (deg > 1) w1 = ld_stream_u32(H.other + rp[1] + t, pol.stream);
-  if (deg > 0) { recA = load_rec(H, (int64_t)rp[0] + t, pol.stream); poseA = gather_pose(xyt, w0, pol.keep); }
-  for (int k = 0; k < deg; k += 2) {
-    uint32_t w2 = 0, w3 = 0;
-    if (k + 1 < deg) { recB = load_rec(H, (int64_t)rp[k + 1] + t, pol.stream); poseB = gather_pose(xyt, w1, pol.keep); }
-    if (k + 2 < deg) w2 = ld_stream_u32(H.other + rp[k + 2] + t, pol.stream);
-    process(w0, recA, poseA, (int64_t)rp[k] + t);
-    if (k + 1 >= deg) break;
-    if (k + 2 < deg) { recA = load_rec(H, (int64_t)rp[k + 2] + t, pol.stream); poseA = gather_pose(xyt, w2, pol.keep); }
-    if (k + 3 < deg) w3 = ld_stream_u32(H.other + rp[k + 3] + t, pol.stream);
-    process(w1, recB, poseB, (int64_t)rp[k + 1] + t);
-    w0 = w2; w1 = w3;
+  // Software pipeline in registers, one round deep and in lockstep.  ptxas tracks every long-latency load of
+  // this loop on ONE scoreboard, so a wait for any loaded value also waits for every load issued before it:
+  // the loads of round k+1 (record, gathered pose, index word of round k+2) are therefore issued at the top of
+  // round k, the round-k math then runs entirely on registers that hold no pending load, and the only
+  // scoreboard wait of the loop is the rotation next -> current at its end.  For the same reason nothing is
+  // re-loaded inside the loop (lane i keeps the start of round i, a shuffle hands it out), the loop is
+  // warp-uniform, and the loads are predicated instructions rather than branches.
+  const int lane = threadIdx.x & 31;
+  const int kmax = __reduce_max_sync(0xffffffffu, deg);
+  for (int base = 0; base < kmax; base += 32) {
+    const int kend = min(kmax, base + 32);
+    const int rpreg = (base + lane < kend) ? rp[base + lane] : 0;
+    auto slot_of = [&](int k) -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, rpreg, k & 31) + t; };
+    uint32_t wC = 0, wN = 0, wNN = 0;
+    HalfEdgeRec recC = {0, 0, 0}, recN = {0, 0, 0};
+    PoseRec poseC = {0, 0, 0}, poseN = {0, 0, 0};
+    int64_t sC = slot_of(base), sN = slot_of(base + 1);
+    ld_stream_u32_if(wC, H.other + sC, pol.stream, base < deg);
+    ld_stream_u32_if(wN, H.other + sN, pol.stream, base + 1 < deg);
+    ld_stream_if(recC.tmx, H.tmx + sC, pol.stream, base < deg);
+    ld_stream_if(recC.tmy, H.tmy + sC, pol.stream, base < deg);
+    ld_stream_if(recC.thm, H.thm + sC, pol.stream, base < deg);
+    ld_keep3_if(poseC.x, poseC.y, poseC.th, xyt + (wC & kIdxMask), pol.keep, base < deg);
+#pragma unroll 1
+    for (int k = base; k < kend; ++k) {
+      const bool on1 = k + 1 < deg && k + 1 < kend;
+      ld_stream_if(recN.tmx, H.tmx + sN, pol.stream, on1);
+      ld_stream_if(recN.tmy, H.tmy + sN, pol.stream, on1);
+      ld_stream_if(recN.thm, H.thm + sN, pol.stream, on1);
+      ld_keep3_if(poseN.x, poseN.y, poseN.th, xyt + (wN & kIdxMask), pol.keep, on1);
+      const int64_t sNN = slot_of(k + 2);
+      ld_stream_u32_if(wNN, H.other + sNN, pol.stream, k + 2 < deg && k + 2 < kend);
+      if (k < deg) process(wC, recC, poseC, sC);
+      wC = wN; wN = wNN; recC = recN; poseC = poseN; sC = sN; sN = sNN;
+    }
   }
   if (has_row) {
     Hdiag[0 * L.ldn + lr] = d00; Hdiag[1 * L.ldn + lr] = d01; Hdiag[2 * L.ldn + lr] = d02;
@@ -167,36 +184,84 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   }
 }
 
-// Deterministic fold of per-task partials (K sums then M maxima, each n long) in task order.
+// Deterministic fold of per-task partials (K sums then M maxima, each n long).  Up to 32 CTAs fold contiguous
+// chunks (all K+M loads of a thread are independent), the CTA that arrives last folds the per-CTA partials with a
+// fixed shuffle tree, so the result does not depend on arrival order.  ws: (K+M)*32 doubles, ticket: one zeroed uint.
 // `rotate_rz`: S_RZ <- S_RZ_NEXT (PCG scalar rotation, see k_pcg_direction).
-constexpr int kFoldThreads = 1024;
+constexpr int kFoldThreads = 256;
+constexpr int kFoldMaxBlocks = 32;
+inline int fold_blocks(int n) { return n <= 4 * kFoldThreads ? 1 : min(kFoldMaxBlocks, (n + 4 * kFoldThreads - 1) / (4 * kFoldThreads)); }
 template <int K, int M>
 __global__ void __launch_bounds__(kFoldThreads)
-k_fold_tasks(const double* __restrict__ part, int n, double* out, double* scal, int rotate_rz) {
-  __shared__ double s_red[kFoldThreads / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int k = 0; k < K + M; ++k) {
-    const bool is_sum = k < K;
-    double a = 0.0;
-    for (int i = threadIdx.x; i < n; i += kFoldThreads) {
-      const double y = part[(size_t)k * n + i];
-      a = is_sum ? a + y : fmax(a, y);
-    }
+k_fold_tasks(const double* __restrict__ part, int n, double* out, double* scal, int rotate_rz, double* ws, unsigned int* ticket) {
+  __shared__ double s_red[K + M][kFoldThreads / 32];
+  __shared__ unsigned int s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nb = gridDim.x;
+  const int chunk = (n + nb - 1) / nb, lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  double a[K + M];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double y = __shfl_xor_sync(0xffffffffu, a, o);
-      a = is_sum ? a + y : fmax(a, y);
-    }
-    __syncthreads();
-    if (lane == 0) s_red[wid] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int w = 0; w < kFoldThreads / 32; ++w) t = is_sum ? t + s_red[w] : fmax(t, s_red[w]);
-      out[k] = t;
+  for (int k = 0; k < K + M; ++k) a[k] = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += kFoldThreads) {
+#pragma unroll
+    for (int k = 0; k < K + M; ++k) {
+      const double y = part[(size_t)k * n + i];
+      a[k] = (k < K) ? a[k] + y : fmax(a[k], y);
     }
   }
-  if (threadIdx.x == 0 && rotate_rz) scal[S_RZ] = scal[S_RZ_NEXT];
+#pragma unroll
+  for (int k = 0; k < K + M; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, a[k], o);
+      a[k] = (k < K) ? a[k] + y : fmax(a[k], y);
+    }
+    if (lane == 0) s_red[k][wid] = a[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < K + M; ++k) {
+      double t = lane < kFoldThreads / 32 ? s_red[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_xor_sync(0xffffffffu, t, o);
+        t = (k < K) ? t + y : fmax(t, y);
+      }
+      a[k] = t;
+    }
+    if (nb == 1) {
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K + M; ++k) out[k] = a[k];
+        if (rotate_rz) scal[S_RZ] = scal[S_RZ_NEXT];
+      }
+      return;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < K + M; ++k) ws[k * kFoldMaxBlocks + blockIdx.x] = a[k];
+      __threadfence();
+      s_last = (atomicAdd(ticket, 1u) == (unsigned)nb - 1u);
+    }
+    __syncwarp();
+    if (s_last) {
+      __threadfence();
+#pragma unroll
+      for (int k = 0; k < K + M; ++k) {
+        double t = lane < nb ? __ldcg(ws + k * kFoldMaxBlocks + lane) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double y = __shfl_xor_sync(0xffffffffu, t, o);
+          t = (k < K) ? t + y : fmax(t, y);
+        }
+        if (lane == 0) out[k] = t;
+      }
+      if (lane == 0) {
+        *ticket = 0u;   // re-arm for the next launch
+        if (rotate_rz) scal[S_RZ] = scal[S_RZ_NEXT];
+      }
+    }
+  }
 }
 
 // Linear-solver setup: the SpMV walks full rows, so every non-owner slot receives the transpose of its

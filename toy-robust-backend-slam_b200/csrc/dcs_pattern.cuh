@@ -161,16 +161,29 @@ __global__ void k_row_ptr(const uint64_t* keys, int32_t nh, int32_t row_lo, int3
 // kWindow = 1024 on the 1M-pose benchmark graph, 86% at 128).
 // pass 1: rank of each row inside its window, max degree per window
 __global__ void __launch_bounds__(kWindow)
-k_jds_rank(const int32_t* row_ptr, int32_t nrows, uint16_t* rank_of, uint16_t* perm, int32_t* win_rounds) {
+k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t* rank_of, uint16_t* perm, int32_t* win_rounds) {
   __shared__ int32_t s_deg[kWindow];
+  __shared__ int32_t s_own[kWindow];
   const int32_t r = blockIdx.x * kWindow + threadIdx.x;
-  const int32_t d = (r < nrows) ? row_ptr[r + 1] - row_ptr[r] : 0;
+  int32_t d = 0, own = 0;
+  if (r < nrows) {
+    const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+    d = e - b;
+    // a row's entries are sorted owner-first: own = how many have the non-owner key bit clear
+    int32_t lo = b, hi = e;
+    while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (keys[mid] & kKeyNonOwner) hi = mid; else lo = mid + 1; }
+    own = lo - b;
+  }
   s_deg[threadIdx.x] = d;
+  s_own[threadIdx.x] = own;
   __syncthreads();
+  // Rank by (degree, owner entries) descending, stable.  The second key makes the lanes that write an
+  // off-diagonal block in round k (own > k) a contiguous run of their slice, so k_linearize's owner-only block
+  // stores fill whole 32-byte sectors instead of scattering 8-byte pieces over every sector of the round.
   int rank = 0;
   for (int u = 0; u < kWindow; ++u) {
-    const int32_t du = s_deg[u];
-    rank += (du > d) || (du == d && u < (int)threadIdx.x);
+    const int32_t du = s_deg[u], ou = s_own[u];
+    rank += (du > d) || (du == d && (ou > own || (ou == own && u < (int)threadIdx.x)));
   }
   rank_of[(int64_t)blockIdx.x * kWindow + threadIdx.x] = (uint16_t)rank;
   perm[(int64_t)blockIdx.x * kWindow + rank] = (uint16_t)threadIdx.x;
