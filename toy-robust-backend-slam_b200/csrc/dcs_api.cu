@@ -229,7 +229,9 @@ struct dcs_handle {
   // pattern
   DevBuf<uint64_t> keys;        // sorted (row<<32|col)
   DevBuf<uint32_t> vals;        // edge<<1|side
-  DevBuf<int32_t> row_ptr, rp_off, round_ptr, slot, up_flag, up_scan, mirror_src;
+  DevBuf<int32_t> row_ptr, rp_off, round_ptr, slot, up_flag, up_scan, expand_src, task_obase;
+  int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
+  DevBuf<double> Hup;          // [9][ldu] upper-triangular off-diagonal blocks in (task, round, lane) order
   bool mirrored = false;       // lower copies of Hoff are current
   DevBuf<uint16_t> rank_of, perm;
   int32_t n_upper = 0;
@@ -271,6 +273,7 @@ struct dcs_handle {
     L.row_lo = 0; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;   // gathered arrays are indexed locally: own rows start at 0
     L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
     L.nwin = nwin; L.ntasks = ntasks;
+    L.task_obase = task_obase.p; L.ldu = ldu;
     return L;
   }
   HalfEdges halfedges() const {
@@ -465,7 +468,7 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 
 // K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
 int linearize(dcs_handle* h, const double4* xyt) {
-  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->Hoff.p, h->Hdiag.p,
+  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->Hup.p, h->Hdiag.p,
          h->grad.p, h->task_part.p);
   k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
@@ -481,7 +484,7 @@ int linearize(dcs_handle* h, const double4* xyt) {
 // linear-solver setup: fill the lower (mirrored) block copies the row-wise SpMV reads
 int ensure_mirror(dcs_handle* h) {
   if (h->mirrored || h->nh == 0) { h->mirrored = true; return DCS_OK; }
-  LAUNCH(k_mirror, cdiv(h->nh, 256), 256, h->stream, h->mirror_src.p, h->nh, h->ldh, h->Hoff.p);
+  LAUNCH(k_expand, cdiv(h->nh, 256), 256, h->stream, h->expand_src.p, h->nh, h->ldh, h->ldu, h->Hup.p, h->Hoff.p);
   h->mirrored = true;
   return DCS_OK;
 }
@@ -782,15 +785,27 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CKS(build_halo(h, nh));      // halo lists + the global -> local index map the half-edge words use
   const size_t HH = (size_t)h->ldh;
   CK(h->h_other.alloc_zero(HH, st)); CK(h->h_tmx.alloc_zero(HH, st)); CK(h->h_tmy.alloc_zero(HH, st)); CK(h->h_thm.alloc_zero(HH, st));
-  CK(h->mirror_src.alloc((size_t)std::max(nh, 1)));
+  CK(h->expand_src.alloc((size_t)std::max(nh, 1)));
+  CK(h->task_obase.alloc_zero((size_t)h->ntasks + 1, st));
   if (nh > 0) {
+    DevBuf<int32_t> mirror_src, cidx;
+    CK(mirror_src.alloc((size_t)nh)); CK(cidx.alloc((size_t)nh));
     DevBuf<int32_t> edge_slot;
     CK(edge_slot.alloc((size_t)2 * EE));
     CK(cudaMemsetAsync(edge_slot.p, 0xFF, (size_t)2 * EE * 4, st));
     LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
            h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->g2l.p, h->h_other.p,
            h->h_tmx.p, h->h_tmy.p, h->h_thm.p, edge_slot.p);
-    LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, h->mirror_src.p);
+    LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, mirror_src.p);
+    // compact owner-block order = the order k_linearize meets the owner half-edges in
+    LAUNCH(k_owner_enum<false>, h->ntasks, kRowsPerBlock, st, h->layout(), h->h_other.p, h->task_obase.p, (int32_t*)nullptr);
+    CKS(scan_exclusive(h->task_obase.p, (int64_t)h->ntasks + 1, st));
+    int32_t n_own = 0;
+    CK(cudaMemcpyAsync(&n_own, h->task_obase.p + h->ntasks, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->ldu = ((int64_t)std::max(n_own, 1) + 31) / 32 * 32;
+    LAUNCH(k_owner_enum<true>, h->ntasks, kRowsPerBlock, st, h->layout(), h->h_other.p, (int32_t*)nullptr, cidx.p);
+    LAUNCH(k_expand_src, cdiv(nh, 256), 256, st, h->h_other.p, mirror_src.p, cidx.p, nh, h->expand_src.p);
     CK(cudaStreamSynchronize(st));
   }
 
@@ -810,7 +825,17 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const size_t LN = (size_t)h->ldn;
   const size_t NL = (size_t)std::max(h->n_loc, 1);
   CK(h->xyt.alloc_zero(NL, st)); CK(h->cand_xyt.alloc_zero(NL, st)); CK(h->p4.alloc_zero(NL, st));
-  CK(h->Hoff.alloc_zero(9 * HH, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
+  if (std::getenv("DCS_L2_PERSIST")) {   // dev probe: pin the gathered pose array in the L2 set-aside
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)64 << 20);
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.base_ptr = h->xyt.p;
+    av.accessPolicyWindow.num_bytes = std::min((size_t)NL * sizeof(double4), (size_t)64 << 20);
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
+  CK(h->Hoff.alloc_zero(9 * HH, st)); CK(h->Hup.alloc_zero(9 * (size_t)h->ldu, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
   CK(h->scale.alloc_zero(3 * LN, st)); CK(h->lmdiag.alloc_zero(3 * LN, st)); CK(h->Adiag.alloc_zero(6 * LN, st)); CK(h->Minv.alloc_zero(6 * LN, st));
   CK(h->w.alloc_zero(3 * LN, st)); CK(h->r.alloc_zero(3 * LN, st)); CK(h->q.alloc_zero(3 * LN, st)); CK(h->z.alloc_zero(3 * LN, st));
   CK(h->lambda_tmp.alloc_zero(3 * LN, st)); CK(h->rhs_tmp.alloc_zero(3 * LN, st));
@@ -1020,6 +1045,7 @@ int dcs_get_hessian(dcs_handle* h, double* block_values) {
   if (nh > 0) {
     DevBuf<double> d_up;
     CK(d_up.alloc_zero(up.size(), h->stream));
+    CKS(ensure_mirror(h));     // slot-order copy of the compact upper blocks
     LAUNCH(k_export_upper, cdiv(nh, 256), 256, h->stream, h->keys.p, h->up_scan.p, h->up_flag.p, h->slot.p, nh, h->Hoff.p, h->ldh, d_up.p);
     CK(cudaMemcpyAsync(up.data(), d_up.p, up.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -31,6 +31,8 @@ struct RowLayout {           // jagged-diagonal layout of the owned rows
   const int32_t* round_ptr;  // first slot of every round
   int32_t nwin;              // windows of kWindow rows
   int32_t ntasks;            // nwin * kSlicesPerWindow warp tasks
+  const int32_t* task_obase; // [ntasks+1] first compact owner-block index of every task
+  int64_t ldu;               // leading dimension of the compact owner-block SoA (Hup)
 };
 
 // Warp task mapping shared by the row-owner kernels: CTA = one warp = slice `sl` (ranks [32 sl, 32 sl + 32))
@@ -77,14 +79,31 @@ __device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, 
 
 // The assembled product is the reference's structure: the upper-triangular block matrix (one 3x3
 // off-diagonal block per edge, written by the half-edge whose row is the smaller endpoint: kFlagOwner),
-// the diagonal blocks and the gradient.  The mirrored (lower) copies the SpMV's full row storage wants
-// are filled by k_mirror as part of the linear-solver setup.
-__global__ void __launch_bounds__(kRowsPerBlock, 20)
+// the diagonal blocks and the gradient.  The owner blocks go to a COMPACT array Hup (9 planes of ldu doubles)
+// in (task, round, lane) order: a task writes one dense run per plane, every 32-byte sector and 128-byte
+// line is written whole (partially written lines cost DRAM the same as full ones: the flat traffic probe
+// writes the 288 MB of owner blocks scattered over the slot space in 80 us, all 576 MB of slots in 92 us).
+// The full row storage the SpMV walks (both triangles, slot order) is filled from Hup by k_expand as part
+// of the linear-solver setup.
+#ifndef DCS_K1_WARPS
+#define DCS_K1_WARPS 20
+#endif
+#ifndef DCS_K1_PIPE       // 0: one-round register pipeline, 1: cp.async ring
+#define DCS_K1_PIPE 0
+#endif
+#ifndef DCS_K1_DIST       // cp.async ring: stream / gather request distances in rounds
+#define DCS_K1_DIST 6
+#endif
+#ifndef DCS_K1_GDIST
+#define DCS_K1_GDIST 3
+#endif
+__global__ void __launch_bounds__(kRowsPerBlock, DCS_K1_WARPS)
 k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
-            double* __restrict__ Hoff, double* __restrict__ Hdiag, double* __restrict__ grad,
+            double* __restrict__ Hup, double* __restrict__ Hdiag, double* __restrict__ grad,
             double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
   const WarpTask wt = warp_task(L);
+  int orun = wt.valid ? L.task_obase[blockIdx.x] : 0;   // compact index of the task's next owner block
   const int t = wt.rank;
   const int lr = wt.lr;
   const bool has_row = wt.valid && lr < L.nrows;
@@ -114,20 +133,29 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     g1 += side_b ? T.bf1 : -T.bf1;
     g2 += side_b ? T.gb : T.ga;
     if (word & kFlagCost) cost += T.cost;
+#ifdef DCS_K1_NOSTORE
+    if ((word & kFlagOwner) && T.cost == 1.2345e300) {
+#else
     if (word & kFlagOwner) {   // off-diagonal block (row pose x other pose)
-      double* out = Hoff + idx;
-      st_stream(out + 0 * L.ldh, -T.U00, pol.stream);
-      st_stream(out + 1 * L.ldh, -T.U01, pol.stream);
-      st_stream(out + 2 * L.ldh, side_b ? T.e0 : -T.sc0, pol.stream);
-      st_stream(out + 3 * L.ldh, -T.U01, pol.stream);
-      st_stream(out + 4 * L.ldh, -T.U11, pol.stream);
-      st_stream(out + 5 * L.ldh, side_b ? T.e1 : -T.sc1, pol.stream);
-      st_stream(out + 6 * L.ldh, side_b ? -T.sc0 : T.e0, pol.stream);
-      st_stream(out + 7 * L.ldh, side_b ? -T.sc1 : T.e1, pol.stream);
-      st_stream(out + 8 * L.ldh, T.o22, pol.stream);
+#endif
+#ifdef DCS_K1_SMALLSTORE   // dev probe: same store instructions, L2-resident target
+      double* out = Hup + (idx & 0xFFFF);
+#else
+      double* out = Hup + idx;
+#endif
+      st_stream(out + 0 * L.ldu, -T.U00, pol.stream);
+      st_stream(out + 1 * L.ldu, -T.U01, pol.stream);
+      st_stream(out + 2 * L.ldu, side_b ? T.e0 : -T.sc0, pol.stream);
+      st_stream(out + 3 * L.ldu, -T.U01, pol.stream);
+      st_stream(out + 4 * L.ldu, -T.U11, pol.stream);
+      st_stream(out + 5 * L.ldu, side_b ? T.e1 : -T.sc1, pol.stream);
+      st_stream(out + 6 * L.ldu, side_b ? -T.sc0 : T.e0, pol.stream);
+      st_stream(out + 7 * L.ldu, side_b ? -T.sc1 : T.e1, pol.stream);
+      st_stream(out + 8 * L.ldu, T.o22, pol.stream);
     }
   };
 
+#if DCS_K1_PIPE == 0
   // Software pipeline in registers, one round deep and in lockstep.  ptxas tracks every long-latency load of
   // this loop on ONE scoreboard, so a wait for any loaded value also waits for every load issued before it:
   // the loads of round k+1 (record, gathered pose, index word of round k+2) are therefore issued at the top of
@@ -154,16 +182,86 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
 #pragma unroll 1
     for (int k = base; k < kend; ++k) {
       const bool on1 = k + 1 < deg && k + 1 < kend;
+#ifndef DCS_K1_NOSTREAM   // (dev probes: timing only, results are wrong with either switch)
       ld_stream_if(recN.tmx, H.tmx + sN, pol.stream, on1);
       ld_stream_if(recN.tmy, H.tmy + sN, pol.stream, on1);
       ld_stream_if(recN.thm, H.thm + sN, pol.stream, on1);
+#endif
+#ifndef DCS_K1_NOGATHER
       ld_keep3_if(poseN.x, poseN.y, poseN.th, xyt + (wN & kIdxMask), pol.keep, on1);
+#else
+      poseN.x = ox + (double)(wN & 7u); poseN.y = oy + 1.0; poseN.th = oth + 0.1;
+#endif
       const int64_t sNN = slot_of(k + 2);
       ld_stream_u32_if(wNN, H.other + sNN, pol.stream, k + 2 < deg && k + 2 < kend);
-      if (k < deg) process(wC, recC, poseC, sC);
+      const unsigned om = __ballot_sync(0xffffffffu, k < deg && (wC & kFlagOwner));
+      if (k < deg) process(wC, recC, poseC, (int64_t)orun + __popc(om & ((1u << lane) - 1u)));
+      orun += __popc(om);
       wC = wN; wN = wNN; recC = recN; poseC = poseN; sC = sN; sN = sNN;
     }
   }
+#else
+  // Software pipeline through shared memory.  Every lane owns a private ring of slots: the index word and the
+  // measurement record of round k + kD and the gathered pose of round k + kG (whose index word has landed by
+  // then) are requested with cp.async at the top of round k, one commit group per round.  Groups retire in
+  // order, so cp.async.wait_group kP guarantees everything requested more than kP rounds ago: each request
+  // has kP full rounds of arithmetic (and every other resident warp) to cover its latency, and no register
+  // waits on a load scoreboard inside the loop.  Round starts come from a register (lane i keeps rp[i]).
+  constexpr int kD = DCS_K1_DIST, kG = DCS_K1_GDIST, kDS = kD + 1, kGS = kG + 1;
+  constexpr int kP = (kD - kG - 1 < kG - 1) ? kD - kG - 1 : kG - 1;
+  static_assert(kP >= 0 && kG >= 1 && kD > kG, "pipeline distances");
+  __shared__ __align__(16) double2 s_pxy[kGS][32];
+  __shared__ double s_pth[kGS][32];
+  __shared__ double s_tmx[kDS][32], s_tmy[kDS][32], s_thm[kDS][32];
+  __shared__ uint32_t s_w[kDS][32];
+  const int lane = threadIdx.x & 31;
+  const int kmax = __reduce_max_sync(0xffffffffu, deg);
+  for (int base = 0; base < kmax; base += 32) {
+    const int kend = min(kmax, base + 32);
+    const int dend = min(deg, kend);               // this lane's rounds of the chunk end here
+    const int rpreg = (base + lane < kend) ? rp[base + lane] : 0;
+    int ss = 0, sc = 0, sgw = 0, sgp = 0, scp = 0;  // ring positions: stream in, current, gather word, gather in, pose current
+    for (int kk = base - kD; kk < kend; ++kk) {
+      cp_async_wait<kP>();
+      const int ks = kk + kD;                       // stream request
+      if (ks < kend) {
+        const bool on = ks < dend;
+        const int64_t sl = (int64_t)__shfl_sync(0xffffffffu, rpreg, ks & 31) + t;
+        cp_async4_if(smem_addr(&s_w[ss][lane]), H.other + sl, pol.stream, on);
+        cp_async8_if(smem_addr(&s_tmx[ss][lane]), H.tmx + sl, pol.stream, on);
+        cp_async8_if(smem_addr(&s_tmy[ss][lane]), H.tmy + sl, pol.stream, on);
+        cp_async8_if(smem_addr(&s_thm[ss][lane]), H.thm + sl, pol.stream, on);
+        ss = (ss + 1 == kDS) ? 0 : ss + 1;
+      }
+      const int kg = kk + kG;                       // gather request: its index word landed kD - kG rounds ago
+      if (kg >= base && kg < kend) {
+        const bool on = kg < dend;
+        const uint32_t wg = on ? s_w[sgw][lane] : 0u;
+        const double4* src = xyt + (wg & kIdxMask);
+        cp_async16_if(smem_addr(&s_pxy[sgp][lane]), src, pol.keep, on);
+        cp_async8_if(smem_addr(&s_pth[sgp][lane]), reinterpret_cast<const double*>(src) + 2, pol.keep, on);
+        sgw = (sgw + 1 == kDS) ? 0 : sgw + 1;
+        sgp = (sgp + 1 == kGS) ? 0 : sgp + 1;
+      }
+      cp_async_commit();
+      if (kk >= base) {
+        const uint32_t wC = (kk < dend) ? s_w[sc][lane] : 0u;
+        const unsigned om = __ballot_sync(0xffffffffu, (wC & kFlagOwner) != 0);
+        const int64_t sl = (int64_t)orun + __popc(om & ((1u << lane) - 1u));
+        orun += __popc(om);
+        if (kk < dend) {
+          const HalfEdgeRec recC = {s_tmx[sc][lane], s_tmy[sc][lane], s_thm[sc][lane]};
+          const double2 pxy = s_pxy[scp][lane];
+          const PoseRec poseC = {pxy.x, pxy.y, s_pth[scp][lane]};
+          process(wC, recC, poseC, sl);
+        }
+        sc = (sc + 1 == kDS) ? 0 : sc + 1;
+        scp = (scp + 1 == kGS) ? 0 : scp + 1;
+      }
+    }
+    cp_async_wait<0>();
+  }
+#endif
   if (has_row) {
     Hdiag[0 * L.ldn + lr] = d00; Hdiag[1 * L.ldn + lr] = d01; Hdiag[2 * L.ldn + lr] = d02;
     Hdiag[3 * L.ldn + lr] = d11; Hdiag[4 * L.ldn + lr] = d12; Hdiag[5 * L.ldn + lr] = d22;
@@ -264,25 +362,63 @@ k_fold_tasks(const double* __restrict__ part, int n, double* out, double* scal, 
   }
 }
 
-// Linear-solver setup: the SpMV walks full rows, so every non-owner slot receives the transpose of its
-// partner's block (mirror_src[slot] = partner slot, or -1 for owner slots / constant partners -> zero).
-__global__ void k_mirror(const int32_t* __restrict__ mirror_src, int32_t nh, int64_t ldh, double* Hoff) {
+// Pattern build: enumerate the owner half-edges exactly as k_linearize meets them (task, round, lane).
+// kWrite = false: own_cnt[task] = owner half-edges of the task; kWrite = true: cidx[slot] = compact index.
+template <bool kWrite>
+__global__ void __launch_bounds__(kRowsPerBlock)
+k_owner_enum(RowLayout L, const uint32_t* __restrict__ other, int32_t* own_cnt, int32_t* cidx) {
+  const WarpTask wt = warp_task(L);
+  const int lane = threadIdx.x & 31;
+  const bool has_row = wt.valid && wt.lr < L.nrows;
+  const int deg = has_row ? L.row_ptr[wt.lr + 1] - L.row_ptr[wt.lr] : 0;
+  const int kmax = __reduce_max_sync(0xffffffffu, deg);
+  int run = (kWrite && wt.valid) ? L.task_obase[blockIdx.x] : 0;
+  for (int k = 0; k < kmax; ++k) {
+    const int64_t s = (int64_t)wt.rp[k] + wt.rank;
+    const bool own = k < deg && (other[s] & kFlagOwner);
+    const unsigned om = __ballot_sync(0xffffffffu, own);
+    if (kWrite && own) cidx[s] = run + __popc(om & ((1u << lane) - 1u));
+    run += __popc(om);
+  }
+  if (!kWrite && lane == 0 && wt.valid) own_cnt[blockIdx.x] = run;
+}
+
+// expand_src[slot]: >= 0 copy compact block, <= -2 transpose compact block (-2 - src), -1 no block
+__global__ void k_expand_src(const uint32_t* __restrict__ other, const int32_t* __restrict__ mirror_src,
+                             const int32_t* __restrict__ cidx, int32_t nh, int32_t* expand_src) {
+  const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nh) return;
+  int32_t src = -1;
+  if (other[s] & kFlagOwner) src = cidx[s];
+  else if (mirror_src[s] >= 0) src = -2 - cidx[mirror_src[s]];
+  expand_src[s] = src;
+}
+
+// Linear-solver setup: the SpMV walks full rows in slot order, so every slot receives its block from the
+// compact upper-triangular array: owner slots a copy, their partners the transpose, the rest zero.
+__global__ void k_expand(const int32_t* __restrict__ expand_src, int32_t nh, int64_t ldh, int64_t ldu,
+                         const double* __restrict__ Hup, double* __restrict__ Hoff) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
-  const int32_t s = mirror_src[i];
-  if (s == -1) return;                 // owner slot: already written by k_linearize
+  const int32_t s = expand_src[i];
   double v[9];
-  if (s >= 0) {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) v[c] = Hoff[(int64_t)c * ldh + s];
-  } else {                             // -2: the other endpoint is constant -> no block
+  if (s == -1) {
 #pragma unroll
     for (int c = 0; c < 9; ++c) v[c] = 0.0;
+  } else {
+    const int64_t j = s >= 0 ? s : -2 - s;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = Hup[(int64_t)c * ldu + j];
   }
+  if (s >= -1) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 9; ++c) Hoff[(int64_t)c * ldh + i] = v[c];
+  } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) Hoff[(int64_t)(3 * r + c) * ldh + i] = v[3 * c + r];
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Hoff[(int64_t)(3 * r + c) * ldh + i] = v[3 * c + r];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
