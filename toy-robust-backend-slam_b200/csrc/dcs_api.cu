@@ -229,7 +229,8 @@ struct dcs_handle {
   // pattern
   DevBuf<uint64_t> keys;        // sorted (row<<32|col)
   DevBuf<uint32_t> vals;        // edge<<1|side
-  DevBuf<int32_t> row_ptr, rp_off, round_ptr, slot, up_flag, up_scan, expand_src, task_obase;
+  DevBuf<int32_t> row_ptr, rp_off, round_ptr, round32, slot, up_flag, up_scan, expand_src, task_obase;
+  DevBuf<uint32_t> rank_info;
   int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
   DevBuf<double> Hup;          // [9][ldu] upper-triangular off-diagonal blocks in (task, round, lane) order
   bool mirrored = false;       // lower copies of Hoff are current
@@ -273,7 +274,7 @@ struct dcs_handle {
     L.row_lo = 0; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;   // gathered arrays are indexed locally: own rows start at 0
     L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
     L.nwin = nwin; L.ntasks = ntasks;
-    L.task_obase = task_obase.p; L.ldu = ldu;
+    L.task_obase = task_obase.p; L.ldu = ldu; L.rank_info = rank_info.p; L.round32 = round32.p;
     return L;
   }
   HalfEdges halfedges() const {
@@ -771,13 +772,14 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   }
   CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
   CK(h->rp_off.alloc_zero((size_t)h->nwin + 1, st));
-  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rp_off.p);
+  CK(h->rank_info.alloc((size_t)h->ldn)); CK(h->round32.alloc((size_t)h->nwin * 32));
+  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rank_info.p, h->rp_off.p);
   CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nwin + 1, st));
   int32_t n_rounds = 0;
   CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nwin, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(h->round_ptr.alloc((size_t)std::max(n_rounds, 1)));
-  LAUNCH(k_jds_rounds, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rp_off.p, h->round_ptr.p);
+  LAUNCH(k_jds_rounds, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rp_off.p, h->round_ptr.p, h->round32.p);
   CK(h->slot.alloc((size_t)std::max(nh, 1)));
   if (nh > 0) LAUNCH(k_jds_slot, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_ptr.p, h->rank_of.p, h->rp_off.p,
                      h->round_ptr.p, h->slot.p);

@@ -31,6 +31,8 @@ struct RowLayout {           // jagged-diagonal layout of the owned rows
   const int32_t* round_ptr;  // first slot of every round
   int32_t nwin;              // windows of kWindow rows
   int32_t ntasks;            // nwin * kSlicesPerWindow warp tasks
+  const uint32_t* rank_info; // [nwin*kWindow] rank -> degree << 10 | local row within the window
+  const int32_t* round32;    // [nwin*32] first 32 round starts of every window
   const int32_t* task_obase; // [ntasks+1] first compact owner-block index of every task
   int64_t ldu;               // leading dimension of the compact owner-block SoA (Hup)
 };
@@ -38,16 +40,23 @@ struct RowLayout {           // jagged-diagonal layout of the owned rows
 // Warp task mapping shared by the row-owner kernels: CTA = one warp = slice `sl` (ranks [32 sl, 32 sl + 32))
 // of degree-sorted window `win`.  Window-major order keeps concurrently running CTAs on neighbouring rows
 // (their gathered operands overlap in L2); within a window the longest slices start first.
-struct WarpTask { int lr; int rank; const int32_t* rp; bool valid; };
+// The task's start-up needs two independent coalesced loads (rank_info, round32) instead of the chain
+// perm -> row_ptr and rp_off -> round_ptr; `rp` (rounds >= 32, and the kernels that index it directly) is
+// only waited for where it is used.
+struct WarpTask { int lr; int rank; int deg; int rp_lane; const int32_t* rp; bool valid; };
 __device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
   WarpTask w;
   const int task = blockIdx.x;
   w.valid = task < L.ntasks;
   const int win = w.valid ? task / kSlicesPerWindow : 0;
   const int sl = w.valid ? task - win * kSlicesPerWindow : 0;
-  w.rank = sl * kSlice + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31;
+  w.rank = sl * kSlice + lane;
   const int64_t slot0 = (int64_t)win * kWindow;
-  w.lr = (int)slot0 + L.perm[slot0 + w.rank];
+  const uint32_t info = L.rank_info[slot0 + w.rank];
+  w.rp_lane = L.round32[win * 32 + lane];
+  w.lr = (int)slot0 + (int)(info & (kWindow - 1));
+  w.deg = (w.valid && w.lr < L.nrows) ? (int)(info >> 10) : 0;
   w.rp = L.round_ptr + L.rp_off[win];
   return w;
 }
@@ -110,7 +119,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   int deg = 0;
   double ox = 0, oy = 0, oth = 0;
   if (has_row) {
-    deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
+    deg = wt.deg;
     const double4 p = ld_keep4(xyt + L.row_lo + lr, pol.keep);
     ox = p.x; oy = p.y; oth = p.z;
   }
@@ -167,7 +176,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   const int kmax = __reduce_max_sync(0xffffffffu, deg);
   for (int base = 0; base < kmax; base += 32) {
     const int kend = min(kmax, base + 32);
-    const int rpreg = (base + lane < kend) ? rp[base + lane] : 0;
+    const int rpreg = base == 0 ? wt.rp_lane : ((base + lane < kend) ? rp[base + lane] : 0);
     auto slot_of = [&](int k) -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, rpreg, k & 31) + t; };
     uint32_t wC = 0, wN = 0, wNN = 0;
     HalfEdgeRec recC = {0, 0, 0}, recN = {0, 0, 0};
@@ -369,8 +378,7 @@ __global__ void __launch_bounds__(kRowsPerBlock)
 k_owner_enum(RowLayout L, const uint32_t* __restrict__ other, int32_t* own_cnt, int32_t* cidx) {
   const WarpTask wt = warp_task(L);
   const int lane = threadIdx.x & 31;
-  const bool has_row = wt.valid && wt.lr < L.nrows;
-  const int deg = has_row ? L.row_ptr[wt.lr + 1] - L.row_ptr[wt.lr] : 0;
+  const int deg = wt.deg;
   const int kmax = __reduce_max_sync(0xffffffffu, deg);
   int run = (kWrite && wt.valid) ? L.task_obase[blockIdx.x] : 0;
   for (int k = 0; k < kmax; ++k) {
@@ -446,7 +454,7 @@ k_cost_rows(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   const int lr = wt.lr;
   double cost = 0.0;
   if (wt.valid && lr < L.nrows) {
-    const int deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
+    const int deg = wt.deg;
     const double4 po = ld_keep4(xyt + L.row_lo + lr, pol.keep);
     for (int k = 0; k < deg; ++k) {
       const int64_t idx = (int64_t)wt.rp[k] + t;
@@ -595,7 +603,7 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
   const int lr = wt.lr;
   double y0 = 0, y1 = 0, y2 = 0, dot = 0;
   if (wt.valid && lr < L.nrows) {
-    const int deg = L.row_ptr[lr + 1] - L.row_ptr[lr];
+    const int deg = wt.deg;
     const double4 p = ld_keep4(p4 + L.row_lo + lr, pol.keep);
     const double a00 = D[0 * L.ldn + lr], a01 = D[1 * L.ldn + lr], a02 = D[2 * L.ldn + lr];
     const double a11 = D[3 * L.ldn + lr], a12 = D[4 * L.ldn + lr], a22 = D[5 * L.ldn + lr];

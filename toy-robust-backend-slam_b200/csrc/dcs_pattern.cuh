@@ -161,7 +161,8 @@ __global__ void k_row_ptr(const uint64_t* keys, int32_t nh, int32_t row_lo, int3
 // kWindow = 1024 on the 1M-pose benchmark graph, 86% at 128).
 // pass 1: rank of each row inside its window, max degree per window
 __global__ void __launch_bounds__(kWindow)
-k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t* rank_of, uint16_t* perm, int32_t* win_rounds) {
+k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t* rank_of, uint16_t* perm, uint32_t* rank_info,
+           int32_t* win_rounds) {
   __shared__ int32_t s_deg[kWindow];
   __shared__ int32_t s_own[kWindow];
   const int32_t r = blockIdx.x * kWindow + threadIdx.x;
@@ -187,11 +188,13 @@ k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t
   }
   rank_of[(int64_t)blockIdx.x * kWindow + threadIdx.x] = (uint16_t)rank;
   perm[(int64_t)blockIdx.x * kWindow + rank] = (uint16_t)threadIdx.x;
+  // what a warp task needs to start, in one coalesced word per rank: local row (10 bits) | degree
+  rank_info[(int64_t)blockIdx.x * kWindow + rank] = ((uint32_t)d << 10) | (uint32_t)threadIdx.x;
   if (rank == 0) win_rounds[blockIdx.x] = d + 1;   // rounds + 1 entries in round_ptr
 }
 // pass 2: round_ptr[rp_off[w] + k] = first JDS slot of round k of window w
 __global__ void __launch_bounds__(kWindow)
-k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32_t* round_ptr) {
+k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32_t* round_ptr, int32_t* round32) {
   __shared__ int32_t s_deg[kWindow];
   const int32_t r0 = blockIdx.x * kWindow;
   const int32_t r = r0 + threadIdx.x;
@@ -205,7 +208,9 @@ k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32
     int32_t s = 0;
     for (int u = 0; u < kWindow; ++u) s += min(s_deg[u], k);
     round_ptr[off + k] = base + s;
+    if (k < 32) round32[blockIdx.x * 32 + k] = base + s;   // first 32 round starts at a fixed stride (no rp_off hop)
   }
+  if ((int)threadIdx.x < 32 && (int)threadIdx.x >= nround) round32[blockIdx.x * 32 + threadIdx.x] = 0;
 }
 // pass 3: sorted CSR position -> JDS slot
 __global__ void k_jds_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, const int32_t* row_ptr,
