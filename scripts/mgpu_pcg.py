@@ -29,6 +29,12 @@ lib.dcs_debug_comm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.dcs_debug_comm(s.h, 50, out)
 if rank == 0:
     print(f"world {world}: halo exchange {out[0]:.1f} us ({out[3]:.1f} MB sent per rank), allreduce(1) {out[1]:.1f} us, allreduce(2) {out[2]:.1f} us", flush=True)
+out6 = (C.c_double * 6)()
+lib.dcs_debug_pcg_stages.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.dcs_debug_pcg_stages(s.h, 50, out6)
+if rank == 0:
+    print(f"world {world}: stages us: spmv+fold {out6[0]:.1f}, allreduce(p.q) {out6[1]:.1f}, chain+fold {out6[2]:.1f}, allreduce(r.z) {out6[3]:.1f}, "
+          f"direction {out6[4]:.1f}, halo {out6[5]:.1f}  sum {sum(out6):.1f}", flush=True)
 s.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -259,6 +259,13 @@ struct dcs_handle {
   DevBuf<double4> halo_send_buf;
   int32_t n_halo = 0, n_loc = 0;                       // local index space = [rows_per_rank own | n_halo halo]
   std::vector<int32_t> halo_send_off, halo_recv_off;   // [world+1] offsets per peer
+  std::vector<int32_t> halo_cnt_all;                   // [world][world]: rank r needs halo_cnt_all[r*W+q] rows of rank q
+  // peer-memory halo push (CUDA IPC): peer bases of the two exchanged arrays, or NCCL send/recv when unavailable
+  bool halo_push = false;
+  HaloPeers peers_p4 = {}, peers_xa = {}, peers_xb = {};   // p, and the two pose buffers (xyt / cand_xyt swap on acceptance)
+  const double4 *ipc_xa = nullptr, *ipc_xb = nullptr;       // the pose buffers as they were when the handles were exchanged
+  std::vector<void*> ipc_opened;
+  DevBuf<float> barrier_buf;
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
@@ -355,6 +362,14 @@ int allreduce_sum(dcs_handle* h, double* d, int count) {
 int halo_exchange(dcs_handle* h, double4* arr) {
   if (h->world == 1) return DCS_OK;
   const int32_t ns = h->halo_send_off[h->world];
+  if (h->halo_push && (arr == h->p4.p || arr == h->ipc_xa || arr == h->ipc_xb)) {
+    // every rank takes the same accept/reject decisions, so "my buffer A" is "buffer A" on every peer
+    const HaloPeers& P = (arr == h->p4.p) ? h->peers_p4 : (arr == h->ipc_xa ? h->peers_xa : h->peers_xb);
+    if (ns > 0) LAUNCH(k_halo_push, cdiv(ns, 256 * kPushPerThread), 256, h->stream, arr, h->halo_send_idx.p, ns, P);
+    // every rank's pushes have landed once all ranks passed this point of their streams
+    CKN(nccl_api().AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, h->stream));
+    return DCS_OK;
+  }
   if (ns > 0) LAUNCH(k_halo_pack, cdiv(ns, 256), 256, h->stream, arr, h->halo_send_idx.p, ns, h->halo_send_buf.p);
   CKN(nccl_api().GroupStart());
   for (int r = 0; r < h->world; ++r) {
@@ -364,6 +379,62 @@ int halo_exchange(dcs_handle* h, double4* arr) {
     if (cr > 0) CKN(nccl_api().Recv(arr + h->rows_per_rank + h->halo_recv_off[r], (size_t)cr * 4, ncclDouble, r, h->comm, h->stream));
   }
   CKN(nccl_api().GroupEnd());
+  return DCS_OK;
+}
+
+// one-time (world > 1): open every peer's p / candidate-pose arrays through CUDA IPC so the halo can be pushed
+// with plain stores over NVLink.  All ranks agree (all-reduce of a flag) on push vs the NCCL send/recv path.
+int setup_halo_push(dcs_handle* h) {
+  const int W = h->world;
+  h->halo_push = false;
+  if (W == 1) return DCS_OK;
+  CK(h->barrier_buf.alloc_zero(4, h->stream));
+  cudaStream_t st = h->stream;
+  const char* mode = std::getenv("DCS_HALO");
+  int ok = (W <= 8 && !(mode && std::strcmp(mode, "nccl") == 0)) ? 1 : 0;
+  struct Pair { cudaIpcMemHandle_t p4, xa, xb; };
+  std::vector<Pair> all((size_t)W);
+  DevBuf<unsigned char> d_all;
+  CK(d_all.alloc(sizeof(Pair) * (size_t)W));
+  Pair mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaIpcGetMemHandle(&mine.p4, h->p4.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.xa, h->xyt.p) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.xb, h->cand_xyt.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  CK(cudaMemcpyAsync(d_all.p + sizeof(Pair) * (size_t)h->rank, &mine, sizeof(Pair), cudaMemcpyHostToDevice, st));
+  CKN(nccl_api().AllGather(d_all.p + sizeof(Pair) * (size_t)h->rank, d_all.p, sizeof(Pair), ncclChar, h->comm, st));
+  CK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Pair) * (size_t)W, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->ipc_xa = h->xyt.p; h->ipc_xb = h->cand_xyt.p;
+  HaloPeers P4 = {}, PA = {}, PB = {};
+  P4.world = PA.world = PB.world = W;
+  for (int r = 0; r <= W; ++r) P4.send_off[r] = PA.send_off[r] = PB.send_off[r] = h->halo_send_off[r];
+  for (int r = 0; r < W && ok; ++r) {
+    if (r == h->rank) continue;
+    void *a = nullptr, *b = nullptr, *c = nullptr;
+    if (cudaIpcOpenMemHandle(&a, all[r].p4, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    h->ipc_opened.push_back(a);
+    if (cudaIpcOpenMemHandle(&b, all[r].xa, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    h->ipc_opened.push_back(b);
+    if (cudaIpcOpenMemHandle(&c, all[r].xb, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    h->ipc_opened.push_back(c);
+    P4.ptr[r] = static_cast<double4*>(a);
+    PA.ptr[r] = static_cast<double4*>(b);
+    PB.ptr[r] = static_cast<double4*>(c);
+    int32_t before = 0;     // rank r's halo is grouped by owner: my slice starts after the owners below me
+    for (int q = 0; q < h->rank; ++q) before += h->halo_cnt_all[(size_t)r * W + q];
+    P4.dst_base[r] = PA.dst_base[r] = PB.dst_base[r] = h->rows_per_rank + before;
+  }
+  // agree: push only if every rank could open every peer
+  float flag = ok ? 0.f : 1.f;
+  CK(cudaMemcpyAsync(h->barrier_buf.p + 1, &flag, 4, cudaMemcpyHostToDevice, st));
+  CKN(nccl_api().AllReduce(h->barrier_buf.p + 1, h->barrier_buf.p + 1, 1, ncclFloat, ncclSum, h->comm, st));
+  CK(cudaMemcpyAsync(&flag, h->barrier_buf.p + 1, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->halo_push = (flag == 0.f);
+  h->peers_p4 = P4; h->peers_xa = PA; h->peers_xb = PB;
+  if (h->opt.verbose && h->rank == 0) std::fprintf(stderr, "[dcs] halo exchange: %s\n", h->halo_push ? "peer-memory push (CUDA IPC over NVLink)" : "ncclSend/ncclRecv");
   return DCS_OK;
 }
 
@@ -403,6 +474,7 @@ int build_halo(dcs_handle* h, int32_t nh) {
   CK(cudaMemcpyAsync(all.data(), cnt_all.p, all.size() * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (int r = 0; r < W; ++r) h->halo_send_off[r + 1] = h->halo_send_off[r] + all[(size_t)r * W + h->rank];   // rank r needs that many of my rows
+  h->halo_cnt_all = all;
   const int32_t ns = h->halo_send_off[W];
   CK(h->halo_send_idx.alloc((size_t)std::max(ns, 1)));
   // swap the index lists: I send each owner the (global) indices I need from it; I receive what each peer needs from me
@@ -660,6 +732,7 @@ void dcs_destroy(dcs_handle* h) {
   if (!h) return;
   cudaSetDevice(h->dev);
   if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
+  for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
   if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_rank_scal) cudaFreeHost(h->h_rank_scal);
@@ -860,6 +933,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
   lap("state alloc");
+  CKS(setup_halo_push(h));
   CKS(upload_poses(h, g->pose_xyt, h->xyt.p));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
@@ -986,6 +1060,42 @@ extern "C" int dcs_debug_comm(dcs_handle* h, int repeats, double* out4) {
   out4[1] = timeit([&] { allreduce_sum(h, h->scal.p + S_PQ, 1); });
   out4[2] = timeit([&] { allreduce_sum(h, h->scal.p + S_TMP, 2); });
   out4[3] = (double)h->halo_send_off[h->world] * 32.0 / 1e6;   // MB sent per exchange
+  return DCS_OK;
+}
+
+// development probe: per-stage device time of the PCG iteration (us, averaged), launched stage by stage with
+// events in between (so launch gaps are included, unlike the CUDA-graph production path).
+// out[0..5] = spmv+fold, all-reduce(p.q), vector kernel+fold, all-reduce(r.z, r.r), direction, halo exchange
+extern "C" int dcs_debug_pcg_stages(dcs_handle* h, int repeats, double* out6) {
+  cudaSetDevice(h->dev);
+  if (!h->have_lin) return DCS_ERR_ARG;
+  cudaEvent_t ev[7];
+  for (auto& e : ev) cudaEventCreate(&e);
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const double* D = h->Adiag.p;
+  for (int it = 0; it < repeats + 3; ++it) {
+    cudaEventRecord(ev[0], h->stream);
+    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->task_part.p);
+    k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1, h->fold_ws.p, h->tickets.p + 6);
+    cudaEventRecord(ev[1], h->stream);
+    CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
+    cudaEventRecord(ev[2], h->stream);
+    LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
+           0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
+    cudaEventRecord(ev[3], h->stream);
+    CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
+    cudaEventRecord(ev[4], h->stream);
+    LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, 0, h->nrows, h->ldn, h->p4.p, h->scal.p);
+    cudaEventRecord(ev[5], h->stream);
+    CKS(halo_exchange(h, h->p4.p));
+    cudaEventRecord(ev[6], h->stream);
+    cudaEventSynchronize(ev[6]);
+    if (it >= 3)
+      for (int s = 0; s < 6; ++s) { float ms = 0; cudaEventElapsedTime(&ms, ev[s], ev[s + 1]); acc[s] += 1e3 * ms; }
+  }
+  for (int s = 0; s < 6; ++s) out6[s] = acc[s] / repeats;
+  for (auto& e : ev) cudaEventDestroy(e);
   return DCS_OK;
 }
 

@@ -262,6 +262,37 @@ __global__ void k_halo_pack(const double4* __restrict__ arr, const int32_t* __re
   if (i < n) buf[i] = arr[idx[i]];
 }
 
+// Halo push over NVLink peer memory: entry j of the send list (own row idx[j]) goes straight into the halo
+// region of the peer that asked for it (peer pointers opened with CUDA IPC; the lists have the same order on
+// both sides, so the destination is dst_base[peer] + position in the peer's slice).  Replaces pack + ncclSend
+// /ncclRecv: one kernel, 32-byte coalesced remote stores, no staging buffer.
+struct HaloPeers {
+  double4* ptr[8];        // peer array base (nullptr for self / unused)
+  int32_t send_off[9];    // slices of the send list per peer
+  int32_t dst_base[8];    // first halo entry in the peer's array that belongs to this rank
+  int32_t world;
+};
+constexpr int kPushPerThread = 4;
+__global__ void __launch_bounds__(256)
+k_halo_push(const double4* __restrict__ arr, const int32_t* __restrict__ idx, int32_t n, HaloPeers P) {
+  const int32_t j0 = blockIdx.x * (256 * kPushPerThread) + threadIdx.x;
+  double4 v[kPushPerThread];
+#pragma unroll
+  for (int u = 0; u < kPushPerThread; ++u) {          // all gathers first (local L2), then the remote stores
+    const int32_t j = j0 + u * 256;
+    if (j < n) v[u] = arr[idx[j]];
+  }
+#pragma unroll
+  for (int u = 0; u < kPushPerThread; ++u) {
+    const int32_t j = j0 + u * 256;
+    if (j >= n) continue;
+    int r = 0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q) r += (q < P.world && j >= P.send_off[q]) ? 1 : 0;
+    P.ptr[r][P.dst_base[r] + (j - P.send_off[r])] = v[u];
+  }
+}
+
 // ---- unique upper pattern (parity hook) ------------------------------------------------------------
 // flag[i] = 1 for the first sorted half-edge of every distinct (row,col) with row < col and col not
 // constant.  (Diagonal entries are added per non-empty row by the caller.)
