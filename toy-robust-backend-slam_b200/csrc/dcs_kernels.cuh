@@ -95,7 +95,10 @@ __device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, 
 // The full row storage the SpMV walks (both triangles, slot order) is filled from Hup by k_expand as part
 // of the linear-solver setup.
 #ifndef DCS_K1_WARPS
-#define DCS_K1_WARPS 20
+#define DCS_K1_WARPS 16
+#endif
+#ifndef DCS_K1_ROUNDS     // register pipeline: rounds per stage
+#define DCS_K1_ROUNDS 2
 #endif
 #ifndef DCS_K1_PIPE       // 0: one-round register pipeline, 1: cp.async ring
 #define DCS_K1_PIPE 0
@@ -172,41 +175,74 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   // scoreboard wait of the loop is the rotation next -> current at its end.  For the same reason nothing is
   // re-loaded inside the loop (lane i keeps the start of round i, a shuffle hands it out), the loop is
   // warp-uniform, and the loads are predicated instructions rather than branches.
+  // kR rounds are fetched and processed per pipeline stage: more bytes in flight per warp and kR rounds of
+  // arithmetic to cover them, at the price of kR sets of staging registers (kR = 2 needs 128 registers/thread).
+  constexpr int kR = DCS_K1_ROUNDS;
   const int lane = threadIdx.x & 31;
   const int kmax = __reduce_max_sync(0xffffffffu, deg);
   for (int base = 0; base < kmax; base += 32) {
     const int kend = min(kmax, base + 32);
+    const int dend = min(deg, kend);                 // this lane's rounds of the chunk end here
     const int rpreg = base == 0 ? wt.rp_lane : ((base + lane < kend) ? rp[base + lane] : 0);
     auto slot_of = [&](int k) -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, rpreg, k & 31) + t; };
-    uint32_t wC = 0, wN = 0, wNN = 0;
-    HalfEdgeRec recC = {0, 0, 0}, recN = {0, 0, 0};
-    PoseRec poseC = {0, 0, 0}, poseN = {0, 0, 0};
-    int64_t sC = slot_of(base), sN = slot_of(base + 1);
-    ld_stream_u32_if(wC, H.other + sC, pol.stream, base < deg);
-    ld_stream_u32_if(wN, H.other + sN, pol.stream, base + 1 < deg);
-    ld_stream_if(recC.tmx, H.tmx + sC, pol.stream, base < deg);
-    ld_stream_if(recC.tmy, H.tmy + sC, pol.stream, base < deg);
-    ld_stream_if(recC.thm, H.thm + sC, pol.stream, base < deg);
-    ld_keep3_if(poseC.x, poseC.y, poseC.th, xyt + (wC & kIdxMask), pol.keep, base < deg);
+    uint32_t wC[kR], wN[kR], wNN[kR];
+    HalfEdgeRec recC[kR], recN[kR];
+    PoseRec poseC[kR], poseN[kR];
+    int64_t sN[kR];
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      wC[u] = wN[u] = wNN[u] = 0u;
+      recC[u] = recN[u] = HalfEdgeRec{0, 0, 0};
+      poseC[u] = poseN[u] = PoseRec{0, 0, 0};
+    }
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      const int64_t sC = slot_of(base + u);
+      const bool on = base + u < dend;
+      ld_stream_u32_if(wC[u], H.other + sC, pol.stream, on);
+      ld_stream_if(recC[u].tmx, H.tmx + sC, pol.stream, on);
+      ld_stream_if(recC[u].tmy, H.tmy + sC, pol.stream, on);
+      ld_stream_if(recC[u].thm, H.thm + sC, pol.stream, on);
+    }
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      sN[u] = slot_of(base + kR + u);
+      ld_stream_u32_if(wN[u], H.other + sN[u], pol.stream, base + kR + u < dend);
+    }
+#pragma unroll
+    for (int u = 0; u < kR; ++u)
+      ld_keep3_if(poseC[u].x, poseC[u].y, poseC[u].th, xyt + (wC[u] & kIdxMask), pol.keep, base + u < dend);
 #pragma unroll 1
-    for (int k = base; k < kend; ++k) {
-      const bool on1 = k + 1 < deg && k + 1 < kend;
+    for (int k = base; k < kend; k += kR) {
+#pragma unroll
+      for (int u = 0; u < kR; ++u) {
+        const bool on1 = k + kR + u < dend;
 #ifndef DCS_K1_NOSTREAM   // (dev probes: timing only, results are wrong with either switch)
-      ld_stream_if(recN.tmx, H.tmx + sN, pol.stream, on1);
-      ld_stream_if(recN.tmy, H.tmy + sN, pol.stream, on1);
-      ld_stream_if(recN.thm, H.thm + sN, pol.stream, on1);
+        ld_stream_if(recN[u].tmx, H.tmx + sN[u], pol.stream, on1);
+        ld_stream_if(recN[u].tmy, H.tmy + sN[u], pol.stream, on1);
+        ld_stream_if(recN[u].thm, H.thm + sN[u], pol.stream, on1);
 #endif
 #ifndef DCS_K1_NOGATHER
-      ld_keep3_if(poseN.x, poseN.y, poseN.th, xyt + (wN & kIdxMask), pol.keep, on1);
+        ld_keep3_if(poseN[u].x, poseN[u].y, poseN[u].th, xyt + (wN[u] & kIdxMask), pol.keep, on1);
 #else
-      poseN.x = ox + (double)(wN & 7u); poseN.y = oy + 1.0; poseN.th = oth + 0.1;
+        poseN[u].x = ox + (double)(wN[u] & 7u); poseN[u].y = oy + 1.0; poseN[u].th = oth + 0.1;
 #endif
-      const int64_t sNN = slot_of(k + 2);
-      ld_stream_u32_if(wNN, H.other + sNN, pol.stream, k + 2 < deg && k + 2 < kend);
-      const unsigned om = __ballot_sync(0xffffffffu, k < deg && (wC & kFlagOwner));
-      if (k < deg) process(wC, recC, poseC, (int64_t)orun + __popc(om & ((1u << lane) - 1u)));
-      orun += __popc(om);
-      wC = wN; wN = wNN; recC = recN; poseC = poseN; sC = sN; sN = sNN;
+      }
+      int64_t sNN[kR];
+#pragma unroll
+      for (int u = 0; u < kR; ++u) {
+        sNN[u] = slot_of(k + 2 * kR + u);
+        ld_stream_u32_if(wNN[u], H.other + sNN[u], pol.stream, k + 2 * kR + u < dend);
+      }
+#pragma unroll
+      for (int u = 0; u < kR; ++u) {
+        const bool on = k + u < dend;
+        const unsigned om = __ballot_sync(0xffffffffu, on && (wC[u] & kFlagOwner));
+        if (on) process(wC[u], recC[u], poseC[u], (int64_t)orun + __popc(om & ((1u << lane) - 1u)));
+        orun += __popc(om);
+      }
+#pragma unroll
+      for (int u = 0; u < kR; ++u) { wC[u] = wN[u]; wN[u] = wNN[u]; recC[u] = recN[u]; poseC[u] = poseN[u]; sN[u] = sNN[u]; }
     }
   }
 #else
