@@ -231,6 +231,7 @@ struct dcs_handle {
   DevBuf<uint32_t> vals;        // edge<<1|side
   DevBuf<int32_t> row_ptr, rp_off, round_ptr, round32, slot, up_flag, up_scan, expand_src, task_obase;
   DevBuf<uint32_t> rank_info;
+  DevBuf<uint2> first_words;
   int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
   DevBuf<double> Hup;          // [9][ldu] upper-triangular off-diagonal blocks in (task, round, lane) order
   bool mirrored = false;       // lower copies of Hoff are current
@@ -281,7 +282,7 @@ struct dcs_handle {
     L.row_lo = 0; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;   // gathered arrays are indexed locally: own rows start at 0
     L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
     L.nwin = nwin; L.ntasks = ntasks;
-    L.task_obase = task_obase.p; L.ldu = ldu; L.rank_info = rank_info.p; L.round32 = round32.p;
+    L.task_obase = task_obase.p; L.ldu = ldu; L.rank_info = rank_info.p; L.round32 = round32.p; L.first_words = first_words.p;
     return L;
   }
   HalfEdges halfedges() const {
@@ -754,6 +755,12 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
       return DCS_ERR_ARG;
     }
   }
+  if (g->n_edges >= (1 << 22)) {   // rank_info packs the degree into 22 bits
+    std::vector<int32_t> deg((size_t)g->n_poses, 0);
+    for (int32_t k = 0; k < g->n_edges; ++k) { ++deg[g->edge_a[k]]; ++deg[g->edge_b[k]]; }
+    for (int32_t d : deg)
+      if (d >= (1 << 22)) { g_err = "dcs_create: a pose with 2^22 or more edges is not supported"; return DCS_ERR_ARG; }
+  }
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (o->device < 0 || o->device >= ndev) { g_err = "dcs_create: no such CUDA device"; return DCS_ERR_CUDA; }
@@ -861,6 +868,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const size_t HH = (size_t)h->ldh;
   CK(h->h_other.alloc_zero(HH, st)); CK(h->h_tmx.alloc_zero(HH, st)); CK(h->h_tmy.alloc_zero(HH, st)); CK(h->h_thm.alloc_zero(HH, st));
   CK(h->expand_src.alloc((size_t)std::max(nh, 1)));
+  CK(h->first_words.alloc_zero((size_t)h->ldn, st));
   CK(h->task_obase.alloc_zero((size_t)h->ntasks + 1, st));
   if (nh > 0) {
     DevBuf<int32_t> mirror_src, cidx;
@@ -872,6 +880,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
            h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->g2l.p, h->h_other.p,
            h->h_tmx.p, h->h_tmy.p, h->h_thm.p, edge_slot.p);
     LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, mirror_src.p);
+    LAUNCH(k_first_words, cdiv(h->ldn, 256), 256, st, h->layout(), h->h_other.p, h->first_words.p);
     // compact owner-block order = the order k_linearize meets the owner half-edges in
     LAUNCH(k_owner_enum<false>, h->ntasks, kRowsPerBlock, st, h->layout(), h->h_other.p, h->task_obase.p, (int32_t*)nullptr);
     CKS(scan_exclusive(h->task_obase.p, (int64_t)h->ntasks + 1, st));

@@ -33,6 +33,7 @@ struct RowLayout {           // jagged-diagonal layout of the owned rows
   int32_t ntasks;            // nwin * kSlicesPerWindow warp tasks
   const uint32_t* rank_info; // [nwin*kWindow] rank -> degree << 10 | local row within the window
   const int32_t* round32;    // [nwin*32] first 32 round starts of every window
+  const uint2* first_words;  // [nwin*kWindow] rank -> half-edge words of rounds 0 and 1 (copies of `other`)
   const int32_t* task_obase; // [ntasks+1] first compact owner-block index of every task
   int64_t ldu;               // leading dimension of the compact owner-block SoA (Hup)
 };
@@ -43,7 +44,7 @@ struct RowLayout {           // jagged-diagonal layout of the owned rows
 // The task's start-up needs two independent coalesced loads (rank_info, round32) instead of the chain
 // perm -> row_ptr and rp_off -> round_ptr; `rp` (rounds >= 32, and the kernels that index it directly) is
 // only waited for where it is used.
-struct WarpTask { int lr; int rank; int deg; int rp_lane; const int32_t* rp; bool valid; };
+struct WarpTask { int lr; int rank; int deg; int rp_lane; const int32_t* rp; bool valid; int64_t slot0; };
 __device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
   WarpTask w;
   const int task = blockIdx.x;
@@ -53,6 +54,7 @@ __device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
   const int lane = threadIdx.x & 31;
   w.rank = sl * kSlice + lane;
   const int64_t slot0 = (int64_t)win * kWindow;
+  w.slot0 = slot0;
   const uint32_t info = L.rank_info[slot0 + w.rank];
   w.rp_lane = L.round32[win * 32 + lane];
   w.lr = (int)slot0 + (int)(info & (kWindow - 1));
@@ -116,6 +118,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   const L2Policy pol = make_l2_policy();
   const WarpTask wt = warp_task(L);
   int orun = wt.valid ? L.task_obase[blockIdx.x] : 0;   // compact index of the task's next owner block
+  const uint2 fw = L.first_words[wt.slot0 + wt.rank];   // words of rounds 0 and 1: the first gathers need no word load
   const int t = wt.rank;
   const int lr = wt.lr;
   const bool has_row = wt.valid && lr < L.nrows;
@@ -195,11 +198,13 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
       recC[u] = recN[u] = HalfEdgeRec{0, 0, 0};
       poseC[u] = poseN[u] = PoseRec{0, 0, 0};
     }
+    static_assert(kR <= 2, "first_words holds two rounds");
 #pragma unroll
     for (int u = 0; u < kR; ++u) {
       const int64_t sC = slot_of(base + u);
       const bool on = base + u < dend;
-      ld_stream_u32_if(wC[u], H.other + sC, pol.stream, on);
+      if (base == 0) wC[u] = on ? (u == 0 ? fw.x : fw.y) : 0u;
+      else ld_stream_u32_if(wC[u], H.other + sC, pol.stream, on);
       ld_stream_if(recC[u].tmx, H.tmx + sC, pol.stream, on);
       ld_stream_if(recC[u].tmy, H.tmy + sC, pol.stream, on);
       ld_stream_if(recC[u].thm, H.thm + sC, pol.stream, on);
@@ -425,6 +430,18 @@ k_owner_enum(RowLayout L, const uint32_t* __restrict__ other, int32_t* own_cnt, 
     run += __popc(om);
   }
   if (!kWrite && lane == 0 && wt.valid) own_cnt[blockIdx.x] = run;
+}
+
+// first_words[window][rank] = the rank's half-edge words of rounds 0 and 1
+__global__ void k_first_words(RowLayout L, const uint32_t* __restrict__ other, uint2* first_words) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)L.nwin * kWindow) return;
+  const int win = (int)(i / kWindow), rank = (int)(i % kWindow);
+  const int deg = (int)(L.rank_info[i] >> 10);
+  uint2 w = make_uint2(0u, 0u);
+  if (deg > 0) w.x = other[(int64_t)L.round32[win * 32 + 0] + rank];
+  if (deg > 1) w.y = other[(int64_t)L.round32[win * 32 + 1] + rank];
+  first_words[i] = w;
 }
 
 // expand_src[slot]: >= 0 copy compact block, <= -2 transpose compact block (-2 - src), -1 no block
