@@ -121,6 +121,54 @@ def test_writer_format(tmp_path):
     assert np.genfromtxt(tmp_path / "n.txt", usecols=(1, 2)).shape == (2, 2)   # what drawer/plot_results.py:28 does
 
 
+def test_parallel_parser_keeps_serial_semantics(tmp_path):
+    """The reader tokenises big files with all host threads; the result must be what a serial pass gives,
+    including the acceptance rule (an edge is kept iff both ids are below the number of vertex lines read
+    before it) across chunk boundaries.  Checked against a plain-Python serial pass and the reference header."""
+    rng = np.random.default_rng(7)
+    V, lines, nodes_seen, keep = 40000, [], 0, []
+    vals = rng.normal(size=(V, 3)) * 100.0
+    order = []          # interleave vertex and edge lines so every chunk holds both
+    for i in range(V):
+        lines.append(f"VERTEX_SE2 {i} {float(vals[i,0])!r} {vals[i,1]:.9g} {vals[i,2]:.17g}")
+        nodes_seen += 1
+        for _ in range(2):
+            a, b = int(rng.integers(0, V)), int(rng.integers(0, V))     # about half of them point at later vertices
+            m = [float(v) for v in rng.normal(size=3)]
+            lines.append(f"EDGE_SE2 {a} {b} {m[0]!r} {m[1]!r} {m[2]!r} 44.721360 0 0 44.721360 0 44.721360")
+            if a < nodes_seen and b < nodes_seen:
+                keep.append((a, b, m[0], m[1], m[2]))
+    text = "\n".join(lines) + "\n"
+    assert len(text) > 8 << 20                                          # several parser threads
+    g = Graph.from_g2o_text(text)
+    assert g.n_poses == V and g.n_edges == len(keep)
+    assert np.array_equal(g.pose_xyt[:, 0], vals[:, 0])                 # repr round-trips exactly
+    odo = [k for k in keep if abs(k[0] - k[1]) < 5]; clo = [k for k in keep if abs(k[0] - k[1]) >= 5]
+    want = np.array(odo + clo)
+    assert np.array_equal(g.edge_a, want[:, 0].astype(np.int32)) and np.array_equal(g.edge_b, want[:, 1].astype(np.int32))
+    assert np.array_equal(g.meas_xyt, want[:, 2:5])
+    # the same file without the forward references (the reference indexes nNodes unchecked) through the
+    # reference's own header, and through the mmap path
+    ok = []
+    seen = 0
+    for ln in lines:
+        if ln.startswith("VERTEX"):
+            seen += 1; ok.append(ln)
+        else:
+            t = ln.split(" ")
+            if int(t[1]) < seen and int(t[2]) < seen:
+                ok.append(ln)
+    path = str(tmp_path / "big.g2o")
+    open(path, "w").write("\n".join(ok) + "\n")
+    f = Graph.from_g2o(path)
+    assert f.counts == g.counts and np.array_equal(f.meas_xyt, g.meas_xyt) and np.array_equal(f.pose_xyt, g.pose_xyt)
+    assert np.array_equal(f.edge_a, g.edge_a) and np.array_equal(f.edge_b, g.edge_b)
+    if have_ref:
+        L, h, counts, pose, ea, eb, meas, kind = _ref_graph(path, 1, 0)
+        assert g.counts == counts and np.array_equal(g.pose_xyt, pose) and np.array_equal(g.edge_a, ea)
+        assert np.array_equal(g.edge_b, eb) and np.array_equal(g.meas_xyt, meas) and np.array_equal(g.kind, kind)
+
+
 def test_synthetic_generator(tmp_path):
     g = Graph.synthetic(5000, 13501, n_bogus=1500)
     assert g.counts == (5000, 4999, 13501, 1500) and g.n_edges == 20000 and g.loops_made == 13501

@@ -14,6 +14,8 @@
 #ifndef DCS_B200_G2O_UTIL_H
 #define DCS_B200_G2O_UTIL_H
 
+#include <algorithm>
+#include <charconv>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -21,7 +23,13 @@
 #include <deque>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "graph.h"
 
@@ -42,52 +50,110 @@ class ReadG2O {
 
   // Returns false when the file cannot be opened (the reference silently yields an empty graph).
   bool read(const std::string& fName) {
-    FILE* fp = std::fopen(fName.c_str(), "rb");
+    // the file is mapped, not copied: at 1 M poses it is ~0.5 GB of text
+    const int fd = ::open(fName.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (::fstat(fd, &st) != 0) { ::close(fd); return false; }
+    const size_t sz = (size_t)st.st_size;
+    if (sz == 0) { ::close(fd); return true; }
+    void* m = ::mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m != MAP_FAILED) {
+      ::madvise(m, sz, MADV_SEQUENTIAL);
+      parse(static_cast<const char*>(m), sz);
+      ::munmap(m, sz);
+      ::close(fd);
+      return true;
+    }
+    ::close(fd);
+    FILE* fp = std::fopen(fName.c_str(), "rb");        // not mappable (pipe, odd filesystem): plain read
     if (!fp) return false;
-    std::fseek(fp, 0, SEEK_END);
-    const long sz = std::ftell(fp);
-    std::fseek(fp, 0, SEEK_SET);
-    std::string buf((size_t)(sz > 0 ? sz : 0), '\0');
-    const size_t got = sz > 0 ? std::fread(&buf[0], 1, (size_t)sz, fp) : 0;
+    std::vector<char> buf(sz);
+    const size_t got = std::fread(buf.data(), 1, sz, fp);
     std::fclose(fp);
-    buf.resize(got);
-    parse(buf);
+    parse(buf.data(), got);
     return true;
   }
 
-  // Parses g2o text already in memory (also used by the tests).
-  void parse(const std::string& text) {
-    const char* s = text.data();
-    const char* end = s + text.size();
-    const char* tok[16];
-    while (s < end) {
-      const char* eol = (const char*)std::memchr(s, '\n', (size_t)(end - s));
-      if (!eol) eol = end;
-      // split on ' ' with compression; a leading space yields an empty first token
-      int nt = 0;
-      const char* q = s;
-      if (q < eol && *q == ' ') { tok[nt++] = q; while (q < eol && *q == ' ') ++q; }
-      while (q < eol && nt < 16) {
-        tok[nt++] = q;
-        while (q < eol && *q != ' ') ++q;
-        while (q < eol && *q == ' ') ++q;
-      }
-      if (nt >= 5 && (tag_is(tok[0], eol, "VERTEX_SE2") || tag_is(tok[0], eol, "VERTEX2"))) {
-        const int idx = (int)std::strtol(tok[1], nullptr, 10);
-        add_node(idx, std::strtod(tok[2], nullptr), std::strtod(tok[3], nullptr), std::strtod(tok[4], nullptr));
-      } else if (nt >= 12 && (tag_is(tok[0], eol, "EDGE_SE2") || tag_is(tok[0], eol, "EDGE2"))) {
-        const int a = (int)std::strtol(tok[1], nullptr, 10);
-        const int b = (int)std::strtol(tok[2], nullptr, 10);
-        if (a >= 0 && b >= 0 && a < (int)nNodes.size() && b < (int)nNodes.size()) {
-          const int type = (std::abs(a - b) < 5) ? ODOMETRY_EDGE : CLOSURE_EDGE;
-          Edge* e = new_edge(nNodes[a], nNodes[b], type);
-          e->setEdgePose(std::strtod(tok[3], nullptr), std::strtod(tok[4], nullptr), std::strtod(tok[5], nullptr));
-          e->setInformationMatrix(std::strtod(tok[6], nullptr), std::strtod(tok[7], nullptr), std::strtod(tok[8], nullptr),
-                                  std::strtod(tok[9], nullptr), std::strtod(tok[10], nullptr), std::strtod(tok[11], nullptr));
-          (type == ODOMETRY_EDGE ? nEdgesOdometry : nEdgesClosure).push_back(e);
+  // Parses g2o text already in memory (also used by the tests).  At 1 M poses the text is ~0.5 GB, so the
+  // lines are tokenised and converted by all host threads (chunks cut at line ends, std::from_chars) into
+  // plain records, which are then turned into nodes / edges sequentially in file order: same results and
+  // the same acceptance rule as a serial reader (an edge is kept iff both ids are below the number of vertex
+  // lines read before it).
+  void parse(const std::string& text) { parse(text.data(), text.size()); }
+
+  void parse(const char* data, size_t size) {
+    struct VRec { int idx; double x, y, th; };
+    struct ERec { int a, b; uint32_t vbefore; double v[9]; };
+    struct Chunk { std::vector<VRec> v; std::vector<ERec> e; size_t n_near = 0; };
+    const char* const end = data + size;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    nt = (unsigned)std::min<size_t>(std::min<unsigned>(nt, 32u), size / (1u << 20) + 1);   // >= 1 MB per thread
+    std::vector<const char*> cut(nt + 1, end);
+    cut[0] = data;
+    for (unsigned c = 1; c < nt; ++c) {
+      const char* q = data + size / nt * c;
+      if (q < cut[c - 1]) q = cut[c - 1];
+      const char* nl = (const char*)std::memchr(q, '\n', (size_t)(end - q));
+      cut[c] = nl ? nl + 1 : end;
+    }
+    std::vector<Chunk> chunks(nt);
+    auto work = [&](unsigned c) {
+      Chunk& ch = chunks[c];
+      const char* s = cut[c];
+      const char* const stop = cut[c + 1];
+      const char* tok[16];
+      uint32_t nv = 0;
+      while (s < stop) {
+        const char* eol = (const char*)std::memchr(s, '\n', (size_t)(stop - s));
+        if (!eol) eol = stop;
+        // split on ' ' with compression; a leading space yields an empty first token
+        int ntok = 0;
+        const char* q = s;
+        if (q < eol && *q == ' ') { tok[ntok++] = q; while (q < eol && *q == ' ') ++q; }
+        while (q < eol && ntok < 16) {
+          tok[ntok++] = q;
+          while (q < eol && *q != ' ') ++q;
+          while (q < eol && *q == ' ') ++q;
         }
+        if (ntok >= 5 && (tag_is(tok[0], eol, "VERTEX_SE2") || tag_is(tok[0], eol, "VERTEX2"))) {
+          ch.v.push_back(VRec{to_int(tok[1], eol), to_double(tok[2], eol), to_double(tok[3], eol), to_double(tok[4], eol)});
+          ++nv;
+        } else if (ntok >= 12 && (tag_is(tok[0], eol, "EDGE_SE2") || tag_is(tok[0], eol, "EDGE2"))) {
+          ERec r;
+          r.a = to_int(tok[1], eol); r.b = to_int(tok[2], eol); r.vbefore = nv;
+          for (int k = 0; k < 9; ++k) r.v[k] = to_double(tok[3 + k], eol);
+          ch.n_near += std::abs(r.a - r.b) < 5;
+          ch.e.push_back(r);
+        }
+        s = eol + 1;
       }
-      s = eol + 1;
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned c = 0; c < nt; ++c) th.emplace_back(work, c);
+      for (auto& t : th) t.join();
+    }
+    size_t tv = 0, te = 0, tn = 0;
+    for (const Chunk& ch : chunks) { tv += ch.v.size(); te += ch.e.size(); tn += ch.n_near; }
+    nNodes.reserve(nNodes.size() + tv);
+    nEdgesOdometry.reserve(nEdgesOdometry.size() + tn);
+    nEdgesClosure.reserve(nEdgesClosure.size() + (te - tn));
+    for (unsigned c = 0; c < nt; ++c) {
+      const Chunk& ch = chunks[c];
+      const long long nodes_before = (long long)nNodes.size();
+      for (const VRec& r : ch.v) add_node(r.idx, r.x, r.y, r.th);
+      for (const ERec& r : ch.e) {
+        const long long avail = nodes_before + r.vbefore;     // vertex lines seen before this edge line
+        if (r.a < 0 || r.b < 0 || r.a >= avail || r.b >= avail) continue;
+        const int type = (std::abs(r.a - r.b) < 5) ? ODOMETRY_EDGE : CLOSURE_EDGE;
+        Edge* e = new_edge(nNodes[r.a], nNodes[r.b], type);
+        e->setEdgePose(r.v[0], r.v[1], r.v[2]);
+        e->setInformationMatrix(r.v[3], r.v[4], r.v[5], r.v[6], r.v[7], r.v[8]);
+        (type == ODOMETRY_EDGE ? nEdgesOdometry : nEdgesClosure).push_back(e);
+      }
     }
   }
 
@@ -135,7 +201,15 @@ class ReadG2O {
     std::cout << "writePoseGraph nodes: " << fname << std::endl;
     FILE* fp = std::fopen(fname.c_str(), "w");
     if (!fp) return;
-    for (const Node* n : nNodes) std::fprintf(fp, "%d %g %g %g\n", n->index, n->p[0], n->p[1], n->p[2]);
+    // "index x y theta", 6 significant digits as operator<< / %g print them
+    write_parallel(fp, nNodes.size(), 96, [&](size_t i, char* p) {
+      const Node* n = nNodes[i];
+      p = put_int(p, n->index); *p++ = ' ';
+      p = put_g(p, n->p[0]); *p++ = ' ';
+      p = put_g(p, n->p[1]); *p++ = ' ';
+      p = put_g(p, n->p[2]); *p++ = '\n';
+      return p;
+    });
     std::fclose(fp);
   }
 
@@ -185,13 +259,66 @@ class ReadG2O {
   std::deque<Node> node_arena_;
   std::deque<Edge> edge_arena_;
 
+  // strtod / strtol semantics (longest valid prefix), through std::from_chars when the token is plain
+  // decimal: both are correctly rounded, so the values are identical; anything from_chars does not take
+  // whole (a sign '+', hex, a stray suffix) goes to the C function.
+  static bool ends_token(const char* p, const char* eol) { return p >= eol || *p == ' ' || *p == '\r' || *p == '\n'; }
+  static double to_double(const char* t, const char* eol) {
+    double v = 0.0;
+    const std::from_chars_result r = std::from_chars(t, eol, v);
+    if (r.ec == std::errc() && ends_token(r.ptr, eol)) return v;
+    return std::strtod(t, nullptr);
+  }
+  static int to_int(const char* t, const char* eol) {
+    int v = 0;
+    const std::from_chars_result r = std::from_chars(t, eol, v);
+    if (r.ec == std::errc() && ends_token(r.ptr, eol)) return v;
+    return (int)std::strtol(t, nullptr, 10);
+  }
+
   static bool tag_is(const char* t, const char* eol, const char* tag) {
     const size_t n = std::strlen(tag);
     return (size_t)(eol - t) >= n && std::memcmp(t, tag, n) == 0 && (t + n == eol || t[n] == ' ');
   }
 
   static void write_edges(FILE* fp, const std::vector<Edge*>& vec) {
-    for (const Edge* e : vec) std::fprintf(fp, "%d %d %d\n", e->a->index, e->b->index, e->edge_type);
+    write_parallel(fp, vec.size(), 40, [&](size_t i, char* p) {
+      const Edge* e = vec[i];
+      p = put_int(p, e->a->index); *p++ = ' ';
+      p = put_int(p, e->b->index); *p++ = ' ';
+      p = put_int(p, e->edge_type); *p++ = '\n';
+      return p;
+    });
+  }
+
+  static char* put_int(char* p, int v) { return std::to_chars(p, p + 12, v).ptr; }
+  // printf("%g"): shortest of %e / %f at 6 significant digits, trailing zeros removed
+  static char* put_g(char* p, double v) { return std::to_chars(p, p + 24, v, std::chars_format::general, 6).ptr; }
+
+  // Formats n lines with all host threads (each into its own buffer, `max_line` bytes bound per line) and
+  // writes the buffers in order.
+  template <class F>
+  static void write_parallel(FILE* fp, size_t n, size_t max_line, F&& line) {
+    if (n == 0) return;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    nt = (unsigned)std::min<size_t>(std::min<unsigned>(nt, 32u), n / 65536 + 1);
+    std::vector<std::vector<char>> bufs(nt);
+    std::vector<size_t> used(nt, 0);
+    auto work = [&](unsigned c) {
+      const size_t lo = n * c / nt, hi = n * (c + 1) / nt;
+      bufs[c].resize((hi - lo) * max_line);
+      char* p = bufs[c].data();
+      for (size_t i = lo; i < hi; ++i) p = line(i, p);
+      used[c] = (size_t)(p - bufs[c].data());
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned c = 0; c < nt; ++c) th.emplace_back(work, c);
+      for (auto& t : th) t.join();
+    }
+    for (unsigned c = 0; c < nt; ++c) std::fwrite(bufs[c].data(), 1, used[c], fp);
   }
 };
 
