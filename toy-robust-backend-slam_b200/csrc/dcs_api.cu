@@ -244,12 +244,10 @@ struct dcs_handle {
   DevBuf<double4> xyt, cand_xyt, p4;
   DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
   DevBuf<double> partials, scal, stage3;   // stage3: N x 3 staging for host<->device AoS
-  DevBuf<double> red_part, red_gpart;      // warp_grid_reduce workspace (row-owner kernels)
   DevBuf<double> rank_scal;                // [world][4] per-rank (cost, gsq, gmax) after k_linearize
   double* h_rank_scal = nullptr;
   double lin_cost = 0, lin_gsq = 0, lin_gmax = 0;
   bool lin_scal_pending = false;           // per-rank scalars not folded into h_scal yet
-  DevBuf<unsigned int> red_tickets;        // [ngroups] group tickets + [1] global ticket
   DevBuf<double> fold_ws;                  // k_fold_tasks per-CTA partials [(K+M) <= 4][32]
   DevBuf<double> task_part;                // [3][ntasks] per-task partial sums of the row-owner kernels
   DevBuf<float> chL, chS;                  // chain-segment preconditioner factors (fp32), step-major
@@ -296,11 +294,6 @@ struct dcs_handle {
     return L;
   }
   int vec_grid() const { return std::max(1, cdiv(nrows, kVecThreads)); }
-  WarpRedWs red() const {
-    WarpRedWs w;
-    w.part = red_part.p; w.gpart = red_gpart.p; w.gticket = red_tickets.p; w.ticket = red_tickets.p + cdiv(nblk, kRedGroup);
-    return w;
-  }
 };
 
 namespace {
@@ -933,9 +926,6 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->chain_idx.alloc_zero(LN, st)); CK(h->chain_cnt.alloc_zero(LN, st));
   if (h->nrows > 0) LAUNCH(k_chain_entries, cdiv(h->nrows, 256), 256, st, h->keys.p, nh, h->row_lo, h->nrows, h->chain_idx.p, h->chain_cnt.p);
   CK(h->task_part.alloc_zero((size_t)3 * std::max(h->nblk, (int32_t)(h->ldn / kChainTile) + 1), st));
-  CK(h->red_part.alloc_zero((size_t)3 * h->nblk, st));
-  CK(h->red_gpart.alloc_zero((size_t)3 * cdiv(h->nblk, kRedGroup), st));
-  CK(h->red_tickets.alloc_zero((size_t)cdiv(h->nblk, kRedGroup) + 1, st));
   CK(h->stage3.alloc_zero((size_t)h->Npad * 3, st));
   CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
   CK(h->rank_scal.alloc_zero((size_t)h->world * 4, st));

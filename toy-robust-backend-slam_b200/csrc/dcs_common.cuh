@@ -427,83 +427,4 @@ __device__ __forceinline__ void grid_reduce_max(double v, double* partials, unsi
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Deterministic grid reduction for one-warp CTAs (the row-owner kernels): every CTA publishes K partial
-// sums (+ M maxima); the last CTA of each group of 64 folds that group, the last group folds the groups.
-// Fixed grouping and fold order -> bit-reproducible; no extra launch.
-// Workspace: part[(K+M) * n], gpart[(K+M) * ngroups], gticket[ngroups], ticket[1] (all zero-initialised).
-// ------------------------------------------------------------------------------------------------
-struct WarpRedWs { double* part; double* gpart; unsigned int* gticket; unsigned int* ticket; };
-constexpr int kRedGroup = 64;
-
-template <int K, int M>
-__device__ __forceinline__ void warp_grid_reduce(const double (&v)[K + M], const WarpRedWs& ws, double* out) {
-  const int lane = threadIdx.x & 31;
-  const unsigned int n = gridDim.x, cta = blockIdx.x;
-  const unsigned int ngroups = (n + kRedGroup - 1) / kRedGroup;
-  double x[K + M];
-#pragma unroll
-  for (int k = 0; k < K + M; ++k) {
-    x[k] = v[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double y = __shfl_xor_sync(0xffffffffu, x[k], o);
-      x[k] = (k < K) ? x[k] + y : fmax(x[k], y);
-    }
-  }
-  unsigned int t = 0;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < K + M; ++k) ws.part[(size_t)k * n + cta] = x[k];
-    __threadfence();
-    t = atomicAdd(ws.gticket + cta / kRedGroup, 1u);
-  }
-  t = __shfl_sync(0xffffffffu, t, 0);
-  const unsigned int g = cta / kRedGroup;
-  const unsigned int gsize = min((unsigned int)kRedGroup, n - g * kRedGroup);
-  if (t != gsize - 1) return;
-  __threadfence();
-  // fold this group's partials: lane l takes entries l and l + 32, then a fixed shuffle tree
-#pragma unroll
-  for (int k = 0; k < K + M; ++k) {
-    const double* p = ws.part + (size_t)k * n + (size_t)g * kRedGroup;
-    double a = (lane < (int)gsize) ? __ldcg(p + lane) : 0.0;
-    const double b = (lane + 32 < (int)gsize) ? __ldcg(p + lane + 32) : 0.0;
-    a = (k < K) ? a + b : fmax(a, b);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double y = __shfl_xor_sync(0xffffffffu, a, o);
-      a = (k < K) ? a + y : fmax(a, y);
-    }
-    x[k] = a;
-  }
-  unsigned int t2 = 0;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < K + M; ++k) ws.gpart[(size_t)k * ngroups + g] = x[k];
-    ws.gticket[g] = 0u;                       // re-arm for the next launch
-    __threadfence();
-    t2 = atomicAdd(ws.ticket, 1u);
-  }
-  t2 = __shfl_sync(0xffffffffu, t2, 0);
-  if (t2 != ngroups - 1) return;
-  __threadfence();
-#pragma unroll
-  for (int k = 0; k < K + M; ++k) {
-    const double* p = ws.gpart + (size_t)k * ngroups;
-    double a = 0.0;
-    for (unsigned int i = lane; i < ngroups; i += 32) {
-      const double y = __ldcg(p + i);
-      a = (k < K) ? a + y : fmax(a, y);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double y = __shfl_xor_sync(0xffffffffu, a, o);
-      a = (k < K) ? a + y : fmax(a, y);
-    }
-    if (lane == 0) out[k] = a;
-  }
-  if (lane == 0) *ws.ticket = 0u;
-}
-
 }  // namespace dcs

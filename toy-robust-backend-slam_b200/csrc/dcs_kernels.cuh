@@ -6,7 +6,9 @@
 //                        half-edges (jagged-diagonal layout -> coalesced), keeps the diagonal
 //                        block and gradient in registers and streams one 3x3 off-diagonal block
 //                        per half-edge.  No atomics, bit-reproducible.
-//   k_cost        K6     cost-only evaluation at a candidate point (thread per edge)
+//   k_cost_rows   K6     cost-only evaluation at a candidate point (same row-owner walk, every edge booked once)
+//   k_pcg_chain          chain-segment preconditioned PCG vector step (k_chain_factor: its factorisation)
+//   k_expand             slot-order (both triangles) block storage for the SpMV from the compact upper blocks
 //   k_edge_eval          per-edge r / J / psi / rho' dump in edge order (parity hook; same math)
 //   k_spmv        K3     q = (H + Lambda) p over the same layout, fused p.q partial reduction
 //   k_pcg_*       K4     fused PCG vector updates + dot products, scalars stay on the device
@@ -526,23 +528,6 @@ k_cost_rows(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
   if ((threadIdx.x & 31) == 0) task_part[blockIdx.x] = cost;
-}
-
-__global__ void __launch_bounds__(kEdgeThreads)
-k_cost(const double4* __restrict__ xyt, EdgeList E, int32_t e_lo, int32_t e_hi, Params P,
-       double* partials, unsigned int* ticket, double* out) {
-  double cost = 0.0;
-  for (int64_t e = (int64_t)e_lo + (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x; e < e_hi;
-       e += (int64_t)gridDim.x * kEdgeThreads) {
-    const int32_t a = E.a[e], b = E.b[e];
-    const double4 pa = xyt[a], pb = xyt[b];
-    double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
-    cost += edge_cost_terms(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ld_stream(E.tmx + e), ld_stream(E.tmy + e),
-                            ld_stream(E.thm + e), E.dcs[e] != 0, P, q00, q01, dxw,
-                            dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1);
-  }
-  double s[1] = {cost};
-  grid_reduce_sum<1, kEdgeThreads>(s, partials, ticket, out);
 }
 
 __global__ void __launch_bounds__(kEdgeThreads)
