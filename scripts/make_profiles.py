@@ -50,7 +50,7 @@ All numbers from `gpurun` boxes (one B200 unless stated), clocks untouched (`--c
 
 ## 1. Bench line (`python bench.py --steps 50 --warmup 5`, not under a profiler) — `profiles/{tag}_bench.json`
 
-* `value` = {bench['value']:.4g} edges/s ({bench['ms_per_step'] * 1e3:.1f} us per step = fused eval+assembly launch + 3 us fold, 1 M poses / 4 M edges, inputs resident)
+* `value` = {bench['value']:.4g} edges/s ({bench['ms_per_step'] * 1e3:.1f} us per step = fused eval+assembly launch + its fold kernel, 1 M poses / 4 M edges, inputs resident)
 * `roofline.frac` = {bench['roofline']['frac']:.3f} of the measured HBM peak ({bench['roofline']['peak']} GB/s); algorithmic bytes 108 E + 120 N = 552 MB per launch, DRAM traffic {traffic / 1e6:.0f} MB
 * `e2e` = {bench['e2e']['value']:.4g} edges/s ({bench['e2e']['ms_per_step']:.2f} ms per C-ABI call: page-locked host poses in (24 MB H2D), launch, scalar result out)
 * `cpu_baseline` = {bench['cpu_baseline']['value']:.4g} edges/s (oracle port, {bench['cpu_baseline']['cores']} host threads)
