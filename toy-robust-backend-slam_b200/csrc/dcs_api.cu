@@ -507,16 +507,24 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// host N x 3 poses -> device packed poses (own rows + halo, local order)
+// host N x 3 poses -> device packed poses (own rows + halo, local order).  With several ranks every rank uploads
+// only its own rows (N / world of the array) and the halo comes from the owners over NVLink, like every other
+// halo exchange; the call is collective, as dcs_linearize / dcs_cost / dcs_solve already are.
 int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt) {
-  const double* src = pose_xyt;
-  if (!is_pinned(pose_xyt)) {       // pageable caller memory: bounce through the handle's pinned buffer
-    std::memcpy(h->h_pin3, pose_xyt, (size_t)h->N * 3 * sizeof(double));
-    src = h->h_pin3;
+  const int32_t own_lo = h->world > 1 ? h->row_lo : 0;
+  const int32_t own_n = h->world > 1 ? std::max(0, std::min(h->rows_per_rank, h->N - h->row_lo)) : h->N;
+  const double* src = pose_xyt + 3 * (size_t)own_lo;
+  if (own_n > 0) {
+    if (!is_pinned(pose_xyt)) {       // pageable caller memory: bounce through the handle's pinned buffer
+      std::memcpy(h->h_pin3, src, (size_t)own_n * 3 * sizeof(double));
+      src = h->h_pin3;
+    }
+    CK(cudaMemcpyAsync(h->stage3.p + 3 * (size_t)own_lo, src, (size_t)own_n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
-  CK(cudaMemcpyAsync(h->stage3.p, src, (size_t)h->N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(k_pack_poses, cdiv(h->n_loc, 256), 256, h->stream, h->stage3.p, h->N, h->row_lo, h->rows_per_rank, h->halo_recv_idx.p,
-         h->n_loc, xyt);
+  const int32_t n_pack = h->world > 1 ? h->rows_per_rank : h->n_loc;
+  LAUNCH(k_pack_poses, cdiv(n_pack, 256), 256, h->stream, h->stage3.p, h->N, h->row_lo, h->rows_per_rank, h->halo_recv_idx.p,
+         n_pack, xyt);
+  CKS(halo_exchange(h, xyt));
   return DCS_OK;
 }
 // own rows of every rank -> host N x 3
