@@ -234,7 +234,7 @@ struct dcs_handle {
   DevBuf<uint2> first_words;
   int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
   DevBuf<double> Hup;          // [9][ldu] upper-triangular off-diagonal blocks in (task, round, lane) order
-  bool mirrored = false;       // lower copies of Hoff are current
+  bool mirrored = false;       // Hoff (slot order, both triangles) has been filled from Hup for the current linearization
   DevBuf<uint16_t> rank_of, perm;
   int32_t n_upper = 0;
   // half-edges (JDS order)
@@ -556,7 +556,7 @@ int linearize(dcs_handle* h, const double4* xyt) {
   return DCS_OK;
 }
 
-// linear-solver setup: fill the lower (mirrored) block copies the row-wise SpMV reads
+// linear-solver setup: fill the slot-order block storage (both triangles) the row-wise SpMV reads from the compact upper blocks
 int ensure_mirror(dcs_handle* h) {
   if (h->mirrored || h->nh == 0) { h->mirrored = true; return DCS_OK; }
   LAUNCH(k_expand, cdiv(h->nh, 256), 256, h->stream, h->expand_src.p, h->nh, h->ldh, h->ldu, h->Hup.p, h->Hoff.p);

@@ -108,7 +108,7 @@ __global__ void k_radix_scatter(const uint64_t* keys_in, const uint32_t* vals_in
 }
 
 // ---- half-edge generation ---------------------------------------------------------------------
-// key = row << 32 | nonowner << 31 | col; val = edge << 1 | side.  Rows outside [row_lo,row_hi) or constant
+// key = row << 32 | nonowner << 27 | col (27 column bits); val = edge << 1 | side.  Rows outside [row_lo,row_hi) or constant
 // rows are not generated.  "Owner" half-edges (col > row: the upper triangle, the blocks k_linearize stores;
 // also blocks whose partner row lives on another rank) sort before a row's other half-edges, so that in the
 // jagged-diagonal layout the early rounds are (almost) all owners and their block stores fill whole sectors.
@@ -230,7 +230,7 @@ __global__ void k_chain_entries(const uint64_t* keys, int32_t nh, int32_t row_lo
                                 int32_t* chain_cnt) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
-  const uint64_t target = ((uint64_t)(uint32_t)(row_lo + r) << 32) | (uint32_t)(row_lo + r + 1);   // owner entry: bit 31 clear
+  const uint64_t target = ((uint64_t)(uint32_t)(row_lo + r) << 32) | (uint32_t)(row_lo + r + 1);   // owner entry: non-owner bit clear
   int32_t lo = 0, hi = nh;
   while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
   int32_t c = 0;
