@@ -213,6 +213,7 @@ struct dcs_handle {
   Params P;
   int32_t N = 0, E = 0, fixed = 0;
   int dev = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // partition (world == 1: everything)
@@ -766,6 +767,8 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(cudaGetDeviceCount(&ndev));
   if (o->device < 0 || o->device >= ndev) { g_err = "dcs_create: no such CUDA device"; return DCS_ERR_CUDA; }
   CK(cudaSetDevice(o->device));
+  int sm_count_ = 148;
+  cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, o->device);
 
   const double t_c0 = now_s();
   auto lap = [&](const char* what) { if (std::getenv("DCS_CREATE_TIMING")) { cudaDeviceSynchronize(); std::fprintf(stderr, "[dcs_create] %-28s %.3f s\n", what, now_s() - t_c0); } };
@@ -774,6 +777,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   h->opt = *o;
   h->opt.nccl_unique_id = nullptr;
   h->dev = o->device;
+  h->sm_count = sm_count_;
   h->P.phi = o->phi; h->P.hub_a = o->huber_delta; h->P.hub_b = o->huber_delta * o->huber_delta;
   h->N = g->n_poses; h->E = g->n_edges; h->fixed = g->fixed_pose;
   h->rank = o->rank; h->world = std::max(1, o->world);

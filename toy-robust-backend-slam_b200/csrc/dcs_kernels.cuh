@@ -118,20 +118,37 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
             double* __restrict__ Hup, double* __restrict__ Hdiag, double* __restrict__ grad,
             double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
-  const WarpTask wt = warp_task(L);
-  int orun = wt.valid ? L.task_obase[blockIdx.x] : 0;   // compact index of the task's next owner block
-  const uint2 fw = L.first_words[wt.slot0 + wt.rank];   // words of rounds 0 and 1: the first gathers need no word load
-  const int t = wt.rank;
-  const int lr = wt.lr;
-  const bool has_row = wt.valid && lr < L.nrows;
+  // What a task needs to start: four independent coalesced words per lane.
+  struct TaskWords { uint32_t info; int rp_lane; uint2 fw; int obase; };
+  auto load_task_words = [&](int task) {
+    TaskWords w;
+    const int win = task / kSlicesPerWindow, sl = task - win * kSlicesPerWindow;
+    const int lane_ = threadIdx.x & 31;
+    const int64_t i = (int64_t)win * kWindow + sl * kSlice + lane_;
+    w.info = L.rank_info[i];
+    w.rp_lane = L.round32[win * 32 + lane_];
+    w.fw = L.first_words[i];                       // words of rounds 0 and 1: the first gathers need no word load
+    w.obase = L.task_obase[task];
+    return w;
+  };
+  // (Persistent warps with next-task prefetch were measured: 261 us instead of 191 - static task striding loses the
+  // hardware scheduler's load balance and the L1/L2 locality of neighbouring tasks.)
+  const int task = blockIdx.x;
+  if (task >= L.ntasks) return;
+  const TaskWords tw = load_task_words(task);
+  const int win = task / kSlicesPerWindow;
+  const int t = (task - win * kSlicesPerWindow) * kSlice + (threadIdx.x & 31);   // rank inside the window
+  const int lr = win * kWindow + (int)(tw.info & (kWindow - 1));
+  const bool has_row = lr < L.nrows;
+  int orun = tw.obase;                              // compact index of the task's next owner block
+  const uint2 fw = tw.fw;
   int deg = 0;
   double ox = 0, oy = 0, oth = 0;
   if (has_row) {
-    deg = wt.deg;
+    deg = (int)(tw.info >> 10);
     const double4 p = ld_keep4(xyt + L.row_lo + lr, pol.keep);
     ox = p.x; oy = p.y; oth = p.z;
   }
-  const int32_t* rp = wt.rp;
   double d00 = 0, d01 = 0, d02 = 0, d11 = 0, d12 = 0, d22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
 
   auto process = [&](uint32_t word, const HalfEdgeRec& r, const PoseRec& pc, int64_t idx) {
@@ -188,7 +205,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   for (int base = 0; base < kmax; base += 32) {
     const int kend = min(kmax, base + 32);
     const int dend = min(deg, kend);                 // this lane's rounds of the chunk end here
-    const int rpreg = base == 0 ? wt.rp_lane : ((base + lane < kend) ? rp[base + lane] : 0);
+    const int rpreg = base == 0 ? tw.rp_lane : ((base + lane < kend) ? (L.round_ptr + L.rp_off[win])[base + lane] : 0);
     auto slot_of = [&](int k) -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, rpreg, k & 31) + t; };
     uint32_t wC[kR], wN[kR], wNN[kR];
     HalfEdgeRec recC[kR], recN[kR];
@@ -271,7 +288,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   for (int base = 0; base < kmax; base += 32) {
     const int kend = min(kmax, base + 32);
     const int dend = min(deg, kend);               // this lane's rounds of the chunk end here
-    const int rpreg = (base + lane < kend) ? rp[base + lane] : 0;
+    const int rpreg = (base + lane < kend) ? (L.round_ptr + L.rp_off[win])[base + lane] : 0;
     int ss = 0, sc = 0, sgw = 0, sgp = 0, scp = 0;  // ring positions: stream in, current, gather word, gather in, pose current
     for (int kk = base - kD; kk < kend; ++kk) {
       cp_async_wait<kP>();
@@ -329,8 +346,8 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    const size_t n = gridDim.x;
-    task_part[blockIdx.x] = r0; task_part[n + blockIdx.x] = r1; task_part[2 * n + blockIdx.x] = r2;
+    const size_t n = L.ntasks;
+    task_part[task] = r0; task_part[n + task] = r1; task_part[2 * n + task] = r2;
   }
 }
 
