@@ -141,15 +141,17 @@ __global__ void k_mirror_src(const uint32_t* __restrict__ vals, const int32_t* _
   mirror_src[s] = src;
 }
 
-__global__ void k_global_to_own(int32_t* idx, int32_t n, int32_t row_lo) {
+// peers ask with global ids -> storage position of the own row
+__global__ void k_global_to_own(int32_t* idx, int32_t n, int32_t row_lo, const uint16_t* rank_of) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) idx[i] -= row_lo;
+  if (i < n) idx[i] = row_pos(rank_of, idx[i] - row_lo);
 }
 
-__global__ void k_is_free(const int32_t* __restrict__ deg_all, int32_t row_lo, int32_t nrows, int32_t fixed, uint8_t* is_free) {
+__global__ void k_is_free(const int32_t* __restrict__ deg_all, int32_t row_lo, int32_t nrows, int32_t fixed,
+                          const uint16_t* __restrict__ rank_of, uint8_t* is_free) {
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
-  is_free[r] = (deg_all[row_lo + r] > 0 && (row_lo + r) != fixed) ? 1 : 0;
+  is_free[row_pos(rank_of, r)] = (deg_all[row_lo + r] > 0 && (row_lo + r) != fixed) ? 1 : 0;
 }
 
 // parity hook: canonical upper pattern values. One thread per flagged (first-of-run) sorted half-edge.
@@ -456,7 +458,7 @@ int build_halo(dcs_handle* h, int32_t nh) {
   h->n_halo = nr;
   h->n_loc = h->rows_per_rank + nr;
   CK(h->halo_recv_idx.alloc((size_t)std::max(nr, 1)));
-  LAUNCH(k_halo_compact, cdiv(NP, 256), 256, st, need.p, scan.p, NP, h->row_lo, h->rows_per_rank, h->halo_recv_idx.p, h->g2l.p);
+  LAUNCH(k_halo_compact, cdiv(NP, 256), 256, st, need.p, scan.p, NP, h->row_lo, h->rows_per_rank, h->rank_of.p, h->halo_recv_idx.p, h->g2l.p);
   if (W == 1) { CK(cudaStreamSynchronize(st)); return DCS_OK; }
   // counts: all-gather the per-owner receive counts of every rank, read column `rank` = what I must send to whom
   DevBuf<int32_t> cnt_all;
@@ -482,7 +484,7 @@ int build_halo(dcs_handle* h, int32_t nh) {
   }
   CKN(nccl_api().GroupEnd());
   CK(h->halo_send_buf.alloc((size_t)std::max(ns, 1)));
-  if (ns > 0) LAUNCH(k_global_to_own, cdiv(ns, 256), 256, st, h->halo_send_idx.p, ns, h->row_lo);   // peers asked with global ids
+  if (ns > 0) LAUNCH(k_global_to_own, cdiv(ns, 256), 256, st, h->halo_send_idx.p, ns, h->row_lo, h->rank_of.p);   // peers asked with global ids
   CK(cudaStreamSynchronize(st));
   return DCS_OK;
 }
@@ -524,13 +526,13 @@ int upload_poses(dcs_handle* h, const double* pose_xyt, double4* xyt) {
   }
   const int32_t n_pack = h->world > 1 ? h->rows_per_rank : h->n_loc;
   LAUNCH(k_pack_poses, cdiv(n_pack, 256), 256, h->stream, h->stage3.p, h->N, h->row_lo, h->rows_per_rank, h->halo_recv_idx.p,
-         n_pack, xyt);
+         h->rank_of.p, n_pack, xyt);
   CKS(halo_exchange(h, xyt));
   return DCS_OK;
 }
 // own rows of every rank -> host N x 3
 int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
-  LAUNCH(k_unpack_poses, cdiv(h->rows_per_rank, 256), 256, h->stream, xyt, h->row_lo, h->rows_per_rank, h->N, h->stage3.p);
+  LAUNCH(k_unpack_poses, cdiv(h->rows_per_rank, 256), 256, h->stream, xyt, h->rank_of.p, h->row_lo, h->rows_per_rank, h->N, h->stage3.p);
   if (h->world > 1) {     // stage3 is Npad x 3: equal slices, in-place all-gather
     char* base = reinterpret_cast<char*>(h->stage3.p);
     const size_t chunk = (size_t)h->rows_per_rank * 24;
@@ -581,7 +583,7 @@ int pcg_iteration(dcs_handle* h, const double* D) {
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
-           0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+           h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches;
   } else {
@@ -602,9 +604,9 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
   LAUNCH(k_precond, h->vec_grid(), 256, h->stream, h->Hdiag.p, h->lmdiag.p, h->scale.p, h->is_free.p, h->nrows, h->ldn, inv_radius,
          lambda_explicit, h->Adiag.p, h->Minv.p);
   if (h->opt.preconditioner == 1) {
-    LAUNCH(k_chain_factor, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->nrows, h->ldn,
+    LAUNCH(k_chain_factor, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->rank_of.p, h->nrows, h->ldn,
            h->ldh, h->chL.p, h->chS.p);
-    LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, 0, h->nrows,
+    LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->perm.p, 0, h->nrows,
            h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches;
@@ -830,7 +832,6 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->deg_all.alloc_zero((size_t)h->Npad, st));
   if (E > 0) LAUNCH(k_pose_degree, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->deg_all.p);
   CK(h->is_free.alloc_zero((size_t)h->ldn, st));
-  if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->is_free.p);
 
   DevBuf<int32_t> he_off;
   CK(he_off.alloc_zero((size_t)E + 1, st));
@@ -859,6 +860,8 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->rp_off.alloc_zero((size_t)h->nwin + 1, st));
   CK(h->rank_info.alloc((size_t)h->ldn)); CK(h->round32.alloc((size_t)h->nwin * 32));
   LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rank_info.p, h->rp_off.p);
+  if (h->nrows > 0)   // per-row arrays live in (window, rank) order from here on
+    if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->rank_of.p, h->is_free.p);
   CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nwin + 1, st));
   int32_t n_rounds = 0;
   CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nwin, 4, cudaMemcpyDeviceToHost, st));
@@ -973,7 +976,7 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
     if (jacobians) CK(dj.alloc((size_t)E * 18));
     if (psi) CK(dp.alloc((size_t)E));
     if (rho1) CK(dq.alloc((size_t)E));
-    LAUNCH(k_edge_eval, cdiv(E, kEdgeThreads), kEdgeThreads, h->stream, h->xyt.p, h->edgelist(), h->P, dr.p, dj.p, dp.p, dq.p);
+    LAUNCH(k_edge_eval, cdiv(E, kEdgeThreads), kEdgeThreads, h->stream, h->xyt.p, h->g2l.p, h->edgelist(), h->P, dr.p, dj.p, dp.p, dq.p);
     if (residuals) CK(cudaMemcpyAsync(residuals, dr.p, (size_t)E * 24, cudaMemcpyDeviceToHost, h->stream));
     if (jacobians) CK(cudaMemcpyAsync(jacobians, dj.p, (size_t)E * 144, cudaMemcpyDeviceToHost, h->stream));
     if (psi) CK(cudaMemcpyAsync(psi, dp.p, (size_t)E * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -983,7 +986,7 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
   if (gradient) {
     std::memset(gradient, 0, (size_t)h->N * 24);
     if (h->nrows > 0) {
-      LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->nrows, h->ldn, h->stage3.p);
+      LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->rank_of.p, h->nrows, h->ldn, h->stage3.p);
       CK(cudaMemcpyAsync(gradient + 3 * (size_t)h->row_lo, h->stage3.p, (size_t)h->nrows * 24, cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
     }
@@ -1000,7 +1003,7 @@ int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* g
   const bool direct = gradient && is_pinned(gradient);
   if (gradient && h->world > 1) std::memset(gradient, 0, (size_t)h->N * 24);
   if (gradient && h->nrows > 0) {
-    LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->nrows, h->ldn, h->stage3.p);
+    LAUNCH(k_soa_to_aos, cdiv(h->nrows, 256), 256, h->stream, h->grad.p, h->rank_of.p, h->nrows, h->ldn, h->stage3.p);
     CK(cudaMemcpyAsync(direct ? gradient + 3 * (size_t)h->row_lo : h->h_pin3, h->stage3.p, (size_t)h->nrows * 24,
                        cudaMemcpyDeviceToHost, h->stream));
   }
@@ -1092,7 +1095,7 @@ extern "C" int dcs_debug_pcg_stages(dcs_handle* h, int repeats, double* out6) {
     CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
     cudaEventRecord(ev[2], h->stream);
     LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
-           0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+           h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     cudaEventRecord(ev[3], h->stream);
     CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
@@ -1121,14 +1124,25 @@ int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost) {
   return DCS_OK;
 }
 
+// host copy of row_pos for the single-rank parity hooks: natural row r -> storage position
+static int host_row_positions(dcs_handle* h, std::vector<int32_t>* pos) {
+  std::vector<uint16_t> rk((size_t)h->ldn);
+  CK(cudaMemcpy(rk.data(), h->rank_of.p, rk.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  pos->resize((size_t)h->N);
+  for (int32_t r = 0; r < h->N; ++r) (*pos)[r] = (r & ~(kWindow - 1)) + (int32_t)rk[r];
+  return DCS_OK;
+}
+
 int dcs_get_pattern(dcs_handle* h, int32_t* n_block_rows, int32_t* nnzb, int32_t* row_ptr, int32_t* col_idx) {
   if (!h) return DCS_ERR_ARG;
   if (h->world != 1) { g_err = "dcs_get_pattern: single-rank handles only"; return DCS_ERR_ARG; }
   CK(cudaSetDevice(h->dev));
-  std::vector<uint8_t> is_free((size_t)h->N);
-  CK(cudaMemcpy(is_free.data(), h->is_free.p, (size_t)h->N, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> is_free_st((size_t)h->ldn), is_free((size_t)h->N);
+  CK(cudaMemcpy(is_free_st.data(), h->is_free.p, is_free_st.size(), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> rpos;
+  CKS(host_row_positions(h, &rpos));
   int32_t n_diag = 0;
-  for (int32_t i = 0; i < h->N; ++i) n_diag += is_free[i];
+  for (int32_t i = 0; i < h->N; ++i) { is_free[i] = is_free_st[rpos[i]]; n_diag += is_free[i]; }
   if (n_block_rows) *n_block_rows = h->N;
   if (nnzb) *nnzb = n_diag + h->n_upper;
   if (!row_ptr || !col_idx) return DCS_OK;
@@ -1159,8 +1173,10 @@ int dcs_get_hessian(dcs_handle* h, double* block_values) {
   if (!h->have_lin) { g_err = "dcs_get_hessian: nothing linearized yet"; return DCS_ERR_ARG; }
   CK(cudaSetDevice(h->dev));
   const int32_t N = h->N, nh = h->nh;
-  std::vector<uint8_t> is_free((size_t)N);
-  CK(cudaMemcpy(is_free.data(), h->is_free.p, (size_t)N, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> is_free_st((size_t)h->ldn);
+  CK(cudaMemcpy(is_free_st.data(), h->is_free.p, is_free_st.size(), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> rpos;
+  CKS(host_row_positions(h, &rpos));
   std::vector<double> hd((size_t)6 * h->ldn), up((size_t)std::max(h->n_upper, 1) * 9);
   CK(cudaMemcpy(hd.data(), h->Hdiag.p, hd.size() * 8, cudaMemcpyDeviceToHost));
   std::vector<uint64_t> keys((size_t)nh);
@@ -1178,9 +1194,10 @@ int dcs_get_hessian(dcs_handle* h, double* block_values) {
   int64_t pos = 0, u = 0;
   size_t i = 0;
   for (int32_t r = 0; r < N; ++r) {
-    if (is_free[r]) {
-      const double d00 = hd[0 * h->ldn + r], d01 = hd[1 * h->ldn + r], d02 = hd[2 * h->ldn + r];
-      const double d11 = hd[3 * h->ldn + r], d12 = hd[4 * h->ldn + r], d22 = hd[5 * h->ldn + r];
+    const int64_t m = rpos[r];          // per-row arrays are stored in (window, rank) order
+    if (is_free_st[m]) {
+      const double d00 = hd[0 * h->ldn + m], d01 = hd[1 * h->ldn + m], d02 = hd[2 * h->ldn + m];
+      const double d11 = hd[3 * h->ldn + m], d12 = hd[4 * h->ldn + m], d22 = hd[5 * h->ldn + m];
       const double blk[9] = {d00, d01, d02, d01, d11, d12, d02, d12, d22};
       std::memcpy(block_values + 9 * pos, blk, sizeof(blk));
       ++pos;
@@ -1201,7 +1218,7 @@ int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double
   auto up3 = [&](const double* src, double* dst_soa) -> int {
     std::memcpy(h->h_pin3, src + 3 * (size_t)h->row_lo, (size_t)nr * 24);
     CK(cudaMemcpyAsync(h->stage3.p, h->h_pin3, (size_t)nr * 24, cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(k_aos_to_soa, cdiv(nr, 256), 256, h->stream, h->stage3.p, nr, h->ldn, dst_soa);
+    LAUNCH(k_aos_to_soa, cdiv(nr, 256), 256, h->stream, h->stage3.p, h->rank_of.p, nr, h->ldn, dst_soa);
     CK(cudaStreamSynchronize(h->stream));
     return DCS_OK;
   };
@@ -1214,7 +1231,7 @@ int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double
   CKS(pcg_solve(h, 0.0, h->lambda_tmp.p, h->rhs_tmp.p, &iters, &rel));
   std::memset(w, 0, (size_t)h->N * 24);
   if (nr > 0) {
-    LAUNCH(k_soa_to_aos, cdiv(nr, 256), 256, h->stream, h->w.p, nr, h->ldn, h->stage3.p);
+    LAUNCH(k_soa_to_aos, cdiv(nr, 256), 256, h->stream, h->w.p, h->rank_of.p, nr, h->ldn, h->stage3.p);
     CK(cudaMemcpyAsync(h->h_pin3, h->stage3.p, (size_t)nr * 24, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     std::memcpy(w + 3 * (size_t)h->row_lo, h->h_pin3, (size_t)nr * 24);

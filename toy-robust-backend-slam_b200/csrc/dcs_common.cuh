@@ -248,6 +248,15 @@ __device__ __forceinline__ void edge_terms(double xa, double ya, double tha,
   T.gb = sae;
 }
 
+// Own rows are STORED in (window, rank) order - the order the row-owner kernels walk them in - so that every
+// per-row array (diagonal blocks, gradient, PCG vectors, own poses) is read and written coalesced by K1 / SpMV.
+// Natural local row r <-> storage position row_pos(rank_of, r); perm is the inverse inside a window.  Real rows
+// occupy the storage positions [0, nrows) (padding rows have degree 0 and rank last), so elementwise kernels
+// are order-agnostic.
+__device__ __forceinline__ int32_t row_pos(const uint16_t* __restrict__ rank_of, int32_t r) {
+  return (r & ~(kWindow - 1)) + (int32_t)rank_of[r];
+}
+
 // ------------------------------------------------------------------------------------------
 // cache-hinted accesses: matrix / half-edge streams are read once per pass (keep them out of
 // L1, first to leave L2); gathered vectors stay cached.

@@ -59,7 +59,7 @@ __device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
   w.slot0 = slot0;
   const uint32_t info = L.rank_info[slot0 + w.rank];
   w.rp_lane = L.round32[win * 32 + lane];
-  w.lr = (int)slot0 + (int)(info & (kWindow - 1));
+  w.lr = (int)slot0 + w.rank;        // rows are stored in (window, rank) order
   w.deg = (w.valid && w.lr < L.nrows) ? (int)(info >> 10) : 0;
   w.rp = L.round_ptr + L.rp_off[win];
   return w;
@@ -138,7 +138,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
   const TaskWords tw = load_task_words(task);
   const int win = task / kSlicesPerWindow;
   const int t = (task - win * kSlicesPerWindow) * kSlice + (threadIdx.x & 31);   // rank inside the window
-  const int lr = win * kWindow + (int)(tw.info & (kWindow - 1));
+  const int lr = win * kWindow + t;                 // rows are stored in (window, rank) order: coalesced row arrays
   const bool has_row = lr < L.nrows;
   int orun = tw.obase;                              // compact index of the task's next owner block
   const uint2 fw = tw.fw;
@@ -548,12 +548,12 @@ k_cost_rows(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
 }
 
 __global__ void __launch_bounds__(kEdgeThreads)
-k_edge_eval(const double4* __restrict__ xyt, EdgeList E, Params P, double* res, double* jac,
+k_edge_eval(const double4* __restrict__ xyt, const int32_t* __restrict__ g2l, EdgeList E, Params P, double* res, double* jac,
             double* psi, double* rho1) {
   const int64_t e = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   if (e >= E.n) return;
   const int32_t a = E.a[e], b = E.b[e];
-  const double4 pa = xyt[a], pb = xyt[b];
+  const double4 pa = xyt[g2l[a]], pb = xyt[g2l[b]];      // global pose id -> position in the stored pose array
   EdgeLin L;
   edge_linearize<true>(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, E.tmx[e], E.tmy[e], E.thm[e], E.dcs[e] != 0, P, L);
   if (res) { res[3 * e] = L.r0; res[3 * e + 1] = L.r1; res[3 * e + 2] = L.r2; }
@@ -573,18 +573,20 @@ k_edge_eval(const double4* __restrict__ xyt, EdgeList E, Params P, double* res, 
 // Device poses live in the rank's LOCAL index space: [own rows | halo poses in global order].  32-byte records: one
 // sector per gather; the whole gathered working set (own + halo) is contiguous and stays L2 resident.
 __global__ void k_pack_poses(const double* __restrict__ xyt3, int32_t n_global, int32_t row_lo, int32_t rows_per_rank,
-                             const int32_t* __restrict__ halo_idx, int32_t n_loc, double4* xyt) {
+                             const int32_t* __restrict__ halo_idx, const uint16_t* __restrict__ rank_of, int32_t n_loc, double4* xyt) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_loc) return;
   const int32_t j = i < rows_per_rank ? row_lo + i : halo_idx[i - rows_per_rank];
-  xyt[i] = j < n_global ? make_double4(xyt3[3 * (int64_t)j], xyt3[3 * (int64_t)j + 1], xyt3[3 * (int64_t)j + 2], 0.0)
+  const int32_t dst = i < rows_per_rank ? row_pos(rank_of, i) : i;
+  xyt[dst] = j < n_global ? make_double4(xyt3[3 * (int64_t)j], xyt3[3 * (int64_t)j + 1], xyt3[3 * (int64_t)j + 2], 0.0)
                         : make_double4(0, 0, 0, 0);
 }
 // own rows -> global N x 3 staging
-__global__ void k_unpack_poses(const double4* __restrict__ xyt, int32_t row_lo, int32_t rows, int32_t n_global, double* xyt3) {
+__global__ void k_unpack_poses(const double4* __restrict__ xyt, const uint16_t* __restrict__ rank_of, int32_t row_lo, int32_t rows,
+                               int32_t n_global, double* xyt3) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows || row_lo + i >= n_global) return;
-  const double4 p = xyt[i];
+  const double4 p = xyt[row_pos(rank_of, i)];
   const int64_t j = row_lo + i;
   xyt3[3 * j] = p.x; xyt3[3 * j + 1] = p.y; xyt3[3 * j + 2] = p.z;
 }
@@ -812,8 +814,8 @@ __device__ __forceinline__ void sym3_inverse(double a00, double a01, double a02,
 // factorisation: S_0 = D_0; L_j = E_{j-1}^T S_{j-1}^-1; S_j = D_j - L_j E_{j-1}   (E_{j-1} = A[j-1, j])
 __global__ void __launch_bounds__(32)
 k_chain_factor(const double* __restrict__ Adiag, const double* __restrict__ Hoff, const int32_t* __restrict__ slot,
-               const int32_t* __restrict__ chain_idx, const int32_t* __restrict__ chain_cnt, int32_t nrows, int64_t ldn, int64_t ldh,
-               float* __restrict__ chL, float* __restrict__ chS) {
+               const int32_t* __restrict__ chain_idx, const int32_t* __restrict__ chain_cnt, const uint16_t* __restrict__ rank_of,
+               int32_t nrows, int64_t ldn, int64_t ldh, float* __restrict__ chL, float* __restrict__ chS) {
   const int lane = threadIdx.x;
   const int64_t tile0 = (int64_t)blockIdx.x * kChainTile;
   double s00 = 1, s01 = 0, s02 = 0, s11 = 1, s12 = 0, s22 = 1;      // S_{j-1}^-1
@@ -821,9 +823,10 @@ k_chain_factor(const double* __restrict__ Adiag, const double* __restrict__ Hoff
     const int64_t row = tile0 + (int64_t)lane * kChainSeg + j;
     const int64_t tr = tile0 + (int64_t)j * 32 + lane;
     double d00 = 1, d01 = 0, d02 = 0, d11 = 1, d12 = 0, d22 = 1;      // padding rows: identity
-    if (row < nrows) {
-      d00 = Adiag[0 * ldn + row]; d01 = Adiag[1 * ldn + row]; d02 = Adiag[2 * ldn + row];
-      d11 = Adiag[3 * ldn + row]; d12 = Adiag[4 * ldn + row]; d22 = Adiag[5 * ldn + row];
+    if (row < nrows) {            // the chain follows the natural pose order; Adiag is stored in (window, rank) order
+      const int64_t m = row_pos(rank_of, (int32_t)row);
+      d00 = Adiag[0 * ldn + m]; d01 = Adiag[1 * ldn + m]; d02 = Adiag[2 * ldn + m];
+      d11 = Adiag[3 * ldn + m]; d12 = Adiag[4 * ldn + m]; d22 = Adiag[5 * ldn + m];
     }
     double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (j > 0 && row < nrows) {
@@ -865,7 +868,8 @@ k_chain_factor(const double* __restrict__ Adiag, const double* __restrict__ Hoff
 template <bool kInit>
 __global__ void __launch_bounds__(32)
 k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free, const double4* __restrict__ p4r,
-            const double* __restrict__ q, const float* __restrict__ chL, const float* __restrict__ chS, int32_t row_lo,
+            const double* __restrict__ q, const float* __restrict__ chL, const float* __restrict__ chS,
+            const uint16_t* __restrict__ perm, int32_t row_lo,
             int32_t nrows, int64_t ldn, double* w, double* r, double* z, double4* p4w, double* task_part, const double* scal) {
   __shared__ double s_v[3][kChainTile + 32];        // index n + n/32: the per-segment walk is conflict-free
   const int lane = threadIdx.x;
@@ -900,8 +904,8 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
     }
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
-      const int n = (i0 + u) * 32 + lane;
-      const int64_t row = tile0 + n;
+      const int64_t row = tile0 + (i0 + u) * 32 + lane;        // storage position (coalesced)
+      const int n = perm[row];                                 // natural row inside the tile: the chain's order
       double r0 = rv[u][0], r1 = rv[u][1], r2 = rv[u][2];
       if (row < nrows) {
         if (kInit) {
@@ -980,9 +984,9 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
     }
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
-      const int n = (i0 + u) * 32 + lane;
-      const int64_t row = tile0 + n;
+      const int64_t row = tile0 + (i0 + u) * 32 + lane;        // storage position
       if (row < nrows) {
+        const int n = perm[row];
         const int sn = n + (n >> 5);
         const double z0 = s_v[0][sn], z1 = s_v[1][sn], z2 = s_v[2][sn];
         z[0 * ldn + row] = z0; z[1 * ldn + row] = z1; z[2 * ldn + row] = z2;
@@ -1045,15 +1049,18 @@ k_xnorm(const double4* __restrict__ xyt, const uint8_t* __restrict__ is_free, in
 }
 
 // SoA [3][ldn] <-> AoS N x 3 (host-facing) for owned rows
-__global__ void k_soa_to_aos(const double* __restrict__ v, int32_t nrows, int64_t ldn, double* out3) {
+// natural-order N x 3 (C-ABI side) <-> storage-order SoA (device side)
+__global__ void k_soa_to_aos(const double* __restrict__ v, const uint16_t* __restrict__ rank_of, int32_t nrows, int64_t ldn, double* out3) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  out3[3 * (int64_t)i] = v[i]; out3[3 * (int64_t)i + 1] = v[ldn + i]; out3[3 * (int64_t)i + 2] = v[2 * ldn + i];
+  const int32_t m = row_pos(rank_of, i);
+  out3[3 * (int64_t)i] = v[m]; out3[3 * (int64_t)i + 1] = v[ldn + m]; out3[3 * (int64_t)i + 2] = v[2 * ldn + m];
 }
-__global__ void k_aos_to_soa(const double* __restrict__ in3, int32_t nrows, int64_t ldn, double* v) {
+__global__ void k_aos_to_soa(const double* __restrict__ in3, const uint16_t* __restrict__ rank_of, int32_t nrows, int64_t ldn, double* v) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  v[i] = in3[3 * (int64_t)i]; v[ldn + i] = in3[3 * (int64_t)i + 1]; v[2 * ldn + i] = in3[3 * (int64_t)i + 2];
+  const int32_t m = row_pos(rank_of, i);
+  v[m] = in3[3 * (int64_t)i]; v[ldn + m] = in3[3 * (int64_t)i + 1]; v[2 * ldn + m] = in3[3 * (int64_t)i + 2];
 }
 
 }  // namespace dcs

@@ -249,11 +249,11 @@ __global__ void k_halo_mark(const uint64_t* keys, int32_t nh, int32_t row_lo, in
 // compaction: list[scan[j]] = j for every marked pose (scan = exclusive scan of need), and the global -> local
 // index map of the rank: own rows first ([0, rows_per_rank)), then the halo in global order
 __global__ void k_halo_compact(const int32_t* need, const int32_t* scan, int32_t n, int32_t row_lo, int32_t rows_per_rank,
-                               int32_t* list, int32_t* g2l) {
+                               const uint16_t* rank_of, int32_t* list, int32_t* g2l) {
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   int32_t l = -1;
-  if (j >= row_lo && j < row_lo + rows_per_rank) l = j - row_lo;
+  if (j >= row_lo && j < row_lo + rows_per_rank) l = row_pos(rank_of, j - row_lo);     // own rows: storage position
   else if (need[j]) { list[scan[j]] = j; l = rows_per_rank + scan[j]; }
   g2l[j] = l;
 }
