@@ -872,6 +872,7 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
             const uint16_t* __restrict__ perm, int32_t row_lo,
             int32_t nrows, int64_t ldn, double* w, double* r, double* z, double4* p4w, double* task_part, const double* scal) {
   __shared__ double s_v[3][kChainTile + 32];        // index n + n/32: the per-segment walk is conflict-free
+  __shared__ uint16_t s_perm[kChainTile];           // storage position -> natural row, kept for phase 4
   const int lane = threadIdx.x;
   const int64_t tile0 = (int64_t)blockIdx.x * kChainTile;
   double alpha = 0.0;
@@ -884,10 +885,12 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
   for (int i0 = 0; i0 < kChainSeg; i0 += kB) {
     double rv[kB][3], qv[kB][3], wv[kB][3];
     double4 pv[kB];
+    int pn[kB];                                                // natural row inside the tile: the chain's order
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
       const int64_t row = tile0 + (i0 + u) * 32 + lane;
       const bool in = row < nrows;
+      pn[u] = perm[row];                                       // with the batch: the stores below could alias it
       if (kInit) {
         const bool f = in && is_free[row] != 0;
 #pragma unroll
@@ -905,7 +908,8 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
       const int64_t row = tile0 + (i0 + u) * 32 + lane;        // storage position (coalesced)
-      const int n = perm[row];                                 // natural row inside the tile: the chain's order
+      const int n = pn[u];
+      s_perm[(i0 + u) * 32 + lane] = (uint16_t)n;
       double r0 = rv[u][0], r1 = rv[u][1], r2 = rv[u][2];
       if (row < nrows) {
         if (kInit) {
@@ -986,7 +990,7 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
     for (int u = 0; u < kB; ++u) {
       const int64_t row = tile0 + (i0 + u) * 32 + lane;        // storage position
       if (row < nrows) {
-        const int n = perm[row];
+        const int n = s_perm[(i0 + u) * 32 + lane];
         const int sn = n + (n >> 5);
         const double z0 = s_v[0][sn], z1 = s_v[1][sn], z2 = s_v[2][sn];
         z[0 * ldn + row] = z0; z[1 * ldn + row] = z1; z[2 * ldn + row] = z2;
