@@ -48,4 +48,16 @@ void ref_write(void* h, const char* nodes, const char* edges) {
   g->writePoseGraph_edges(edges);
   std::cout.rdbuf(old);
 }
+// METHOD 2 writer (g2o_util.h:114-148): priors / optimised switch values per loop edge (closure, then bogus)
+void ref_write_switches(void* h, const char* path, const double* priors, const double* optimized, int n) {
+  std::ostringstream sink;
+  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+  ReadG2O* g = (ReadG2O*)h;
+  std::vector<double> pr(priors, priors + n);
+  std::vector<double> vals(optimized, optimized + n);
+  std::vector<double*> opt;
+  for (int i = 0; i < n; ++i) opt.push_back(&vals[i]);
+  g->writePoseGraph_switches(path, pr, opt);
+  std::cout.rdbuf(old);
+}
 }

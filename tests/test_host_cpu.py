@@ -121,6 +121,28 @@ def test_writer_format(tmp_path):
     assert np.genfromtxt(tmp_path / "n.txt", usecols=(1, 2)).shape == (2, 2)   # what drawer/plot_results.py:28 does
 
 
+@pytest.mark.skipif(not have_ref, reason="reference checkout / oracle/_ref not present")
+def test_switches_writer_matches_reference(tmp_path):
+    """METHOD 2's switches.txt (reference g2o_util.h:114-148): same bytes from the host writer."""
+    path = f"{REF_DATA}/INTEL.g2o"
+    L, h, counts, *_ = _ref_graph(path, 1, 20)
+    n = counts[2] + counts[3]
+    rng = np.random.default_rng(5)
+    priors = np.ones(n)
+    opt = np.clip(rng.normal(0.7, 0.4, n), -0.2, 1.3)
+    opt[:3] = [1.0, 0.0, 1e-7]
+    L.ref_write_switches.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+    ref_f, mine_f = str(tmp_path / "ref_sw.txt"), str(tmp_path / "sw.txt")
+    L.ref_write_switches(h, ref_f.encode(), priors.ctypes.data_as(C.c_void_p), opt.ctypes.data_as(C.c_void_p), n)
+    host = D.load_host_library()
+    hh = host.dcs_host_read_g2o(path.encode())
+    host.dcs_host_add_random_C(hh, 20, 1, 1)
+    host.dcs_host_write_switches(hh, mine_f.encode(), priors.ctypes.data_as(C.c_void_p), opt.ctypes.data_as(C.c_void_p), n)
+    host.dcs_host_free(hh)
+    assert filecmp.cmp(mine_f, ref_f, shallow=False)
+    assert open(mine_f).readline() == "Odometry EDGES AHEAD\n"
+
+
 def test_parallel_parser_keeps_serial_semantics(tmp_path):
     """The reader tokenises big files with all host threads; the result must be what a serial pass gives,
     including the acceptance rule (an edge is kept iff both ids are below the number of vertex lines read

@@ -131,6 +131,8 @@ def load_host_library():
     lib.dcs_host_set_poses.restype = None
     lib.dcs_host_write_nodes.argtypes = [vp, C.c_char_p]
     lib.dcs_host_write_edges.argtypes = [vp, C.c_char_p]
+    lib.dcs_host_write_switches.argtypes = [vp, C.c_char_p, vp, vp, C.c_int32]
+    lib.dcs_host_write_switches.restype = None
     lib.dcs_host_write_g2o.argtypes = [vp, C.c_char_p]
     lib.dcs_host_free.argtypes = [vp]
     lib.dcs_host_free.restype = None

@@ -223,6 +223,36 @@ class ReadG2O {
     std::fclose(fp);
   }
 
+  // METHOD 2 output (reference :114-148): one line per edge, "a b type prior switch"; odometry edges carry 1 1,
+  // loop edges (closure first, then bogus) the prior and the optimised switch value, 6 significant digits.
+  void writePoseGraph_switches(const std::string& fname, const std::vector<double>& priors, const std::vector<double>& optimized) {
+    std::cout << "#Closure Edges : " << nEdgesClosure.size() << std::endl;
+    std::cout << "#Bogus Edges : " << nEdgesBogus.size() << std::endl;
+    std::cout << "#priors : " << priors.size() << std::endl;
+    std::cout << "#optimized " << optimized.size() << std::endl;
+    FILE* fp = std::fopen(fname.c_str(), "w");
+    if (!fp) return;
+    auto section = [&](const char* title, const std::vector<Edge*>& vec, long offset) {
+      std::fputs(title, fp);
+      write_parallel(fp, vec.size(), 96, [&](size_t i, char* p) {
+        const Edge* e = vec[i];
+        const size_t k = (size_t)(offset + (long)i);
+        const double pr = offset < 0 ? 1.0 : (k < priors.size() ? priors[k] : 0.0);
+        const double sw = offset < 0 ? 1.0 : (k < optimized.size() ? optimized[k] : 0.0);
+        p = put_int(p, e->a->index); *p++ = ' ';
+        p = put_int(p, e->b->index); *p++ = ' ';
+        p = put_int(p, e->edge_type); *p++ = ' ';
+        p = put_g(p, pr); *p++ = ' ';
+        p = put_g(p, sw); *p++ = '\n';
+        return p;
+      });
+    };
+    section("Odometry EDGES AHEAD\n", nEdgesOdometry, -1);
+    section("Closure EDGES AHEAD\n", nEdgesClosure, 0);
+    section("BOGUS EDGES AHEAD\n", nEdgesBogus, (long)nEdgesClosure.size());
+    std::fclose(fp);
+  }
+
   // AoS -> SoA in the residual-block order of the reference's main.cpp:95-150.
   void flatten(FlatGraph* g) const {
     const size_t N = nNodes.size();

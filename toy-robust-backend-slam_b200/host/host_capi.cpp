@@ -86,6 +86,10 @@ void dcs_host_set_poses(dcs_host_graph* h, const double* pose_xyt) {
 
 void dcs_host_write_nodes(dcs_host_graph* h, const char* path) { CoutSilencer s(true); h->g.writePoseGraph_nodes(path); }
 void dcs_host_write_edges(dcs_host_graph* h, const char* path) { CoutSilencer s(true); h->g.writePoseGraph_edges(path); }
+void dcs_host_write_switches(dcs_host_graph* h, const char* path, const double* priors, const double* optimized, int32_t n) {
+  CoutSilencer s(true);
+  h->g.writePoseGraph_switches(path, std::vector<double>(priors, priors + n), std::vector<double>(optimized, optimized + n));
+}
 int dcs_host_write_g2o(dcs_host_graph* h, const char* path) { return synth::write_g2o(h->g, path) ? 0 : 1; }
 void dcs_host_free(dcs_host_graph* h) { delete h; }
 
