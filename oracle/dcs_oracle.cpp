@@ -639,6 +639,29 @@ void oracle_edge_closed_form(const double* pa, const double* pb, const double* m
   if (psi_out) *psi_out = psi;
 }
 
+// SwitchableClosureResidue (ceres_error.cpp:238-297): the plain functor's diff, then e = s * (...) with s the
+// seventh Jet parameter.  Jet product rule h.v = f.a g.v + f.v g.a with f = s: pose partials s * d.v + 0 * d.a,
+// switch partial s * 0 + 1 * d.a - written out so the floating-point operations are the reference's.
+void oracle_sc_edge(const double* pa, const double* pb, const double* meas, double s, double* e, double* J) {
+  const Meas q = make_meas(meas[0], meas[1], meas[2]);
+  Jet P1[3], P2[3], d[3], ps;
+  for (int i = 0; i < 3; ++i) { P1[i] = Jet(pa[i], i); P2[i] = Jet(pb[i], 3 + i); }
+  functor<Jet>(q, false, 0.5, P1, P2, d, &ps);
+  for (int i = 0; i < 3; ++i) {
+    e[i] = s * d[i].a;
+    if (J) {
+      for (int j = 0; j < 6; ++j) J[7 * i + j] = s * d[i].v[j] + 0.0 * d[i].a;
+      J[7 * i + 6] = s * 0.0 + 1.0 * d[i].a;
+    }
+  }
+}
+// SwitchPriorResidue (:300-317): T(sqrt(lambda)) * (T(1) - S[0])
+void oracle_sc_prior(double lambda, double s, double* e, double* J) {
+  const double w = std::sqrt(lambda);
+  e[0] = w * (1.0 - s);
+  if (J) J[0] = w * (0.0 - 1.0) + 0.0 * (1.0 - s);
+}
+
 int oracle_pattern(const oracle_problem* p, int32_t* nnzb, int32_t* row_ptr, int32_t* col_idx) {
   if (!check_problem(p)) return 1;
   Structure S;

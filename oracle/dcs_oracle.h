@@ -77,6 +77,13 @@ int oracle_cost(const oracle_problem* p, const double* pose_xyt, double* cost);
 void oracle_edge_closed_form(const double* pa, const double* pb, const double* meas, int dcs,
                              double phi, double* e, double* J, double* psi);
 
+/* METHOD 2 (switchable constraints, src/ceres_error.cpp:199-317) — per-edge arithmetic only, pinned against the
+ * reference functor; the minimiser for METHOD 2 is not restated yet.
+ * e[3] = s * e_plain; J[21] = 3x7 row-major, columns P1[0..2], P2[0..2], s.  Uncorrected (no loss). */
+void oracle_sc_edge(const double* pa, const double* pb, const double* meas, double s, double* e, double* J);
+/* prior row sqrt(lambda) * (1 - s): e[1], J[1]. */
+void oracle_sc_prior(double lambda, double s, double* e, double* J);
+
 /* Upper block pattern {(i,i)} U {(min,max)} over non-constant, touched poses (CSR over
  * poses).  Pass NULL arrays to query nnzb. */
 int oracle_pattern(const oracle_problem* p, int32_t* nnzb, int32_t* row_ptr, int32_t* col_idx);

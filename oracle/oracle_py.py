@@ -166,3 +166,43 @@ def ref_edges(kind, meas, pa, pb, jac=True):
     rc = R.ref_edges(C.c_int(n), _ptr(kind), _ptr(meas), _ptr(pa), _ptr(pb), _ptr(e), _ptr(J))
     assert rc == 0
     return e, J
+
+
+def sc_edge(pa, pb, meas, s):
+    """METHOD 2 per-edge restatement (oracle_sc_edge): e[3], J[3,7] (P1, P2, s), no loss."""
+    pa = np.ascontiguousarray(pa, dtype=np.float64); pb = np.ascontiguousarray(pb, dtype=np.float64)
+    meas = np.ascontiguousarray(meas, dtype=np.float64)
+    e = np.empty(3); J = np.empty((3, 7))
+    L = lib()
+    L.oracle_sc_edge.restype = None
+    L.oracle_sc_edge(_ptr(pa), _ptr(pb), _ptr(meas), C.c_double(s), _ptr(e), _ptr(J))
+    return e, J
+
+
+def sc_prior(lam, s):
+    e = np.empty(1); J = np.empty(1)
+    L = lib()
+    L.oracle_sc_prior.restype = None
+    L.oracle_sc_prior(C.c_double(lam), C.c_double(s), _ptr(e), _ptr(J))
+    return e[0], J[0]
+
+
+def ref_sc_edge(pa, pb, meas, s):
+    """The REFERENCE's compiled SwitchableClosureResidue through the shim (None when oracle/_ref is absent)."""
+    R = ref_lib()
+    if R is None:
+        return None
+    pa = np.ascontiguousarray(pa, dtype=np.float64); pb = np.ascontiguousarray(pb, dtype=np.float64)
+    meas = np.ascontiguousarray(meas, dtype=np.float64)
+    e = np.empty(3); J = np.empty((3, 7))
+    assert R.ref_switchable_edge(_ptr(meas), _ptr(pa), _ptr(pb), C.c_double(s), _ptr(e), _ptr(J)) == 0
+    return e, J
+
+
+def ref_sc_prior(lam, s):
+    R = ref_lib()
+    if R is None:
+        return None
+    e = np.empty(1); J = np.empty(1)
+    assert R.ref_switch_prior(C.c_double(lam), C.c_double(s), _ptr(e), _ptr(J)) == 0
+    return e[0], J[0]

@@ -185,3 +185,33 @@ def test_multithreaded_oracle_matches_serial():
     a = O.Oracle(g, dcs_on=True, num_threads=1).hessian()
     b = O.Oracle(g, dcs_on=True, num_threads=4).hessian()
     assert np.allclose(a[2], b[2], rtol=1e-13, atol=1e-15) and np.allclose(a[3], b[3], rtol=1e-13, atol=1e-15)
+
+
+def test_switchable_constraint_functors_match_reference():
+    """METHOD 2 groundwork: the per-edge restatement of SwitchableClosureResidue / SwitchPriorResidue
+    (reference src/ceres_error.cpp:199-317) is bit-identical to the reference's own compiled functors."""
+    rng = np.random.default_rng(11)
+    checked = 0
+    for _ in range(400):
+        pa = rng.normal(0, 20, 3); pb = pa + rng.normal(0, 2, 3); meas = rng.normal(0, 1, 3)
+        pa[2] = rng.uniform(-3.1, 3.1); pb[2] = rng.uniform(-3.1, 3.1); meas[2] = rng.uniform(-1.5, 1.5)
+        s = float(rng.uniform(-0.2, 1.3))
+        e, J = O.sc_edge(pa, pb, meas, s)
+        # structure: e = s * e_plain, d e / d s = e_plain, pose columns = s * plain Jacobian
+        e0, J0 = O.sc_edge(pa, pb, meas, 1.0)
+        assert np.allclose(e, s * e0, rtol=1e-15, atol=0) and np.array_equal(J[:, 6], e0)
+        assert np.allclose(J[:, :6], s * J0[:, :6], rtol=1e-15, atol=0)
+        ref = O.ref_sc_edge(pa, pb, meas, s)
+        if ref is not None:
+            assert np.array_equal(e, ref[0]) and np.array_equal(J, ref[1])
+            checked += 1
+    lam = 1.0
+    for s in (1.0, 0.3, -0.1, 1.2):
+        e, J = O.sc_prior(lam, s)
+        assert e == np.sqrt(lam) * (1.0 - s) and J == -np.sqrt(lam)
+        ref = O.ref_sc_prior(lam, s)
+        if ref is not None:
+            assert ref == (e, J)
+    if O.ref_lib() is not None:
+        assert checked == 400
+
