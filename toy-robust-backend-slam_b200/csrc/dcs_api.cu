@@ -917,16 +917,6 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const size_t LN = (size_t)h->ldn;
   const size_t NL = (size_t)std::max(h->n_loc, 1);
   CK(h->xyt.alloc_zero(NL, st)); CK(h->cand_xyt.alloc_zero(NL, st)); CK(h->p4.alloc_zero(NL, st));
-  if (std::getenv("DCS_L2_PERSIST")) {   // dev probe: pin the gathered pose array in the L2 set-aside
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)64 << 20);
-    cudaStreamAttrValue av = {};
-    av.accessPolicyWindow.base_ptr = h->xyt.p;
-    av.accessPolicyWindow.num_bytes = std::min((size_t)NL * sizeof(double4), (size_t)64 << 20);
-    av.accessPolicyWindow.hitRatio = 1.0f;
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-  }
   CK(h->Hoff.alloc_zero(9 * HH, st)); CK(h->Hup.alloc_zero(9 * (size_t)h->ldu, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
   CK(h->scale.alloc_zero(3 * LN, st)); CK(h->lmdiag.alloc_zero(3 * LN, st)); CK(h->Adiag.alloc_zero(6 * LN, st)); CK(h->Minv.alloc_zero(6 * LN, st));
   CK(h->w.alloc_zero(3 * LN, st)); CK(h->r.alloc_zero(3 * LN, st)); CK(h->q.alloc_zero(3 * LN, st)); CK(h->z.alloc_zero(3 * LN, st));

@@ -279,13 +279,7 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
   return v;
 }
 __device__ __forceinline__ void st_stream(double* p, double v, uint64_t pol) {
-#if defined(DCS_ST_PLAIN)
-  asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-#elif defined(DCS_ST_CS)
-  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-#else
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
-#endif
 }
 // gathered operands (poses, the PCG direction vector): small, reused by every row that references them
 __device__ __forceinline__ double4 ld_keep4(const double4* p, uint64_t pol) {
@@ -306,32 +300,10 @@ __device__ __forceinline__ void ld_stream_u32_if(uint32_t& v, const uint32_t* p,
 }
 __device__ __forceinline__ void ld_keep3_if(double& x, double& y, double& z, const double4* p, uint64_t pol, bool on) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-#ifdef DCS_K1_PLAINGATHER
-               "@q ld.global.nc.v2.f64 {%0, %1}, [%3];\n\t"
-               "@q ld.global.nc.f64 %2, [%3+16];\n\t}"
-#else
                "@q ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%3], %4;\n\t"
                "@q ld.global.nc.L2::cache_hint.f64 %2, [%3+16], %4;\n\t}"
-#endif
                : "+d"(x), "+d"(y), "+d"(z) : "l"(p), "l"(pol), "r"((int)on));
 }
-// Asynchronous global -> shared copies (LDGSTS): their completion is tracked by commit groups, which retire in
-// order and can be waited for by COUNT (cp.async.wait_group N), unlike register loads, which all share one
-// scoreboard in the row-owner kernels.  That makes a multi-round prefetch possible.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-#define DCS_CP_ASYNC_IF(NAME, MOD, BYTES)                                                                              \
-  __device__ __forceinline__ void NAME(uint32_t dst, const void* src, uint64_t pol, bool on) {                         \
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"                                                   \
-                 "@q cp.async." MOD ".shared.global.L2::cache_hint [%0], [%1], " #BYTES ", %2;\n\t}"                   \
-                 ::"r"(dst), "l"(src), "l"(pol), "r"((int)on) : "memory");                                             \
-  }
-DCS_CP_ASYNC_IF(cp_async4_if, "ca", 4)
-DCS_CP_ASYNC_IF(cp_async8_if, "ca", 8)
-DCS_CP_ASYNC_IF(cp_async16_if, "cg", 16)
-#undef DCS_CP_ASYNC_IF
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ double2 ld_keep2(const double2* p, uint64_t pol) {
   double2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));

@@ -98,20 +98,13 @@ __device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, 
 // writes the 288 MB of owner blocks scattered over the slot space in 80 us, all 576 MB of slots in 92 us).
 // The full row storage the SpMV walks (both triangles, slot order) is filled from Hup by k_expand as part
 // of the linear-solver setup.
+// 16 resident one-warp CTAs per SM (128 registers per thread), two rounds per pipeline stage: measured best
+// (profiles/r01_kernels.md lists the other occupancy / depth combinations and the cp.async-ring pipeline).
 #ifndef DCS_K1_WARPS
 #define DCS_K1_WARPS 16
 #endif
-#ifndef DCS_K1_ROUNDS     // register pipeline: rounds per stage
+#ifndef DCS_K1_ROUNDS     // rounds fetched and processed per pipeline stage (1 or 2)
 #define DCS_K1_ROUNDS 2
-#endif
-#ifndef DCS_K1_PIPE       // 0: one-round register pipeline, 1: cp.async ring
-#define DCS_K1_PIPE 0
-#endif
-#ifndef DCS_K1_DIST       // cp.async ring: stream / gather request distances in rounds
-#define DCS_K1_DIST 6
-#endif
-#ifndef DCS_K1_GDIST
-#define DCS_K1_GDIST 3
 #endif
 __global__ void __launch_bounds__(kRowsPerBlock, DCS_K1_WARPS)
 k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
@@ -167,16 +160,8 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     g1 += side_b ? T.bf1 : -T.bf1;
     g2 += side_b ? T.gb : T.ga;
     if (word & kFlagCost) cost += T.cost;
-#ifdef DCS_K1_NOSTORE
-    if ((word & kFlagOwner) && T.cost == 1.2345e300) {
-#else
     if (word & kFlagOwner) {   // off-diagonal block (row pose x other pose)
-#endif
-#ifdef DCS_K1_SMALLSTORE   // dev probe: same store instructions, L2-resident target
-      double* out = Hup + (idx & 0xFFFF);
-#else
       double* out = Hup + idx;
-#endif
       st_stream(out + 0 * L.ldu, -T.U00, pol.stream);
       st_stream(out + 1 * L.ldu, -T.U01, pol.stream);
       st_stream(out + 2 * L.ldu, side_b ? T.e0 : -T.sc0, pol.stream);
@@ -189,7 +174,6 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     }
   };
 
-#if DCS_K1_PIPE == 0
   // Software pipeline in registers, one round deep and in lockstep.  ptxas tracks every long-latency load of
   // this loop on ONE scoreboard, so a wait for any loaded value also waits for every load issued before it:
   // the loads of round k+1 (record, gathered pose, index word of round k+2) are therefore issued at the top of
@@ -241,16 +225,10 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
 #pragma unroll
       for (int u = 0; u < kR; ++u) {
         const bool on1 = k + kR + u < dend;
-#ifndef DCS_K1_NOSTREAM   // (dev probes: timing only, results are wrong with either switch)
         ld_stream_if(recN[u].tmx, H.tmx + sN[u], pol.stream, on1);
         ld_stream_if(recN[u].tmy, H.tmy + sN[u], pol.stream, on1);
         ld_stream_if(recN[u].thm, H.thm + sN[u], pol.stream, on1);
-#endif
-#ifndef DCS_K1_NOGATHER
         ld_keep3_if(poseN[u].x, poseN[u].y, poseN[u].th, xyt + (wN[u] & kIdxMask), pol.keep, on1);
-#else
-        poseN[u].x = ox + (double)(wN[u] & 7u); poseN[u].y = oy + 1.0; poseN[u].th = oth + 0.1;
-#endif
       }
       int64_t sNN[kR];
 #pragma unroll
@@ -269,68 +247,6 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
       for (int u = 0; u < kR; ++u) { wC[u] = wN[u]; wN[u] = wNN[u]; recC[u] = recN[u]; poseC[u] = poseN[u]; sN[u] = sNN[u]; }
     }
   }
-#else
-  // Software pipeline through shared memory.  Every lane owns a private ring of slots: the index word and the
-  // measurement record of round k + kD and the gathered pose of round k + kG (whose index word has landed by
-  // then) are requested with cp.async at the top of round k, one commit group per round.  Groups retire in
-  // order, so cp.async.wait_group kP guarantees everything requested more than kP rounds ago: each request
-  // has kP full rounds of arithmetic (and every other resident warp) to cover its latency, and no register
-  // waits on a load scoreboard inside the loop.  Round starts come from a register (lane i keeps rp[i]).
-  constexpr int kD = DCS_K1_DIST, kG = DCS_K1_GDIST, kDS = kD + 1, kGS = kG + 1;
-  constexpr int kP = (kD - kG - 1 < kG - 1) ? kD - kG - 1 : kG - 1;
-  static_assert(kP >= 0 && kG >= 1 && kD > kG, "pipeline distances");
-  __shared__ __align__(16) double2 s_pxy[kGS][32];
-  __shared__ double s_pth[kGS][32];
-  __shared__ double s_tmx[kDS][32], s_tmy[kDS][32], s_thm[kDS][32];
-  __shared__ uint32_t s_w[kDS][32];
-  const int lane = threadIdx.x & 31;
-  const int kmax = __reduce_max_sync(0xffffffffu, deg);
-  for (int base = 0; base < kmax; base += 32) {
-    const int kend = min(kmax, base + 32);
-    const int dend = min(deg, kend);               // this lane's rounds of the chunk end here
-    const int rpreg = (base + lane < kend) ? (L.round_ptr + L.rp_off[win])[base + lane] : 0;
-    int ss = 0, sc = 0, sgw = 0, sgp = 0, scp = 0;  // ring positions: stream in, current, gather word, gather in, pose current
-    for (int kk = base - kD; kk < kend; ++kk) {
-      cp_async_wait<kP>();
-      const int ks = kk + kD;                       // stream request
-      if (ks < kend) {
-        const bool on = ks < dend;
-        const int64_t sl = (int64_t)__shfl_sync(0xffffffffu, rpreg, ks & 31) + t;
-        cp_async4_if(smem_addr(&s_w[ss][lane]), H.other + sl, pol.stream, on);
-        cp_async8_if(smem_addr(&s_tmx[ss][lane]), H.tmx + sl, pol.stream, on);
-        cp_async8_if(smem_addr(&s_tmy[ss][lane]), H.tmy + sl, pol.stream, on);
-        cp_async8_if(smem_addr(&s_thm[ss][lane]), H.thm + sl, pol.stream, on);
-        ss = (ss + 1 == kDS) ? 0 : ss + 1;
-      }
-      const int kg = kk + kG;                       // gather request: its index word landed kD - kG rounds ago
-      if (kg >= base && kg < kend) {
-        const bool on = kg < dend;
-        const uint32_t wg = on ? s_w[sgw][lane] : 0u;
-        const double4* src = xyt + (wg & kIdxMask);
-        cp_async16_if(smem_addr(&s_pxy[sgp][lane]), src, pol.keep, on);
-        cp_async8_if(smem_addr(&s_pth[sgp][lane]), reinterpret_cast<const double*>(src) + 2, pol.keep, on);
-        sgw = (sgw + 1 == kDS) ? 0 : sgw + 1;
-        sgp = (sgp + 1 == kGS) ? 0 : sgp + 1;
-      }
-      cp_async_commit();
-      if (kk >= base) {
-        const uint32_t wC = (kk < dend) ? s_w[sc][lane] : 0u;
-        const unsigned om = __ballot_sync(0xffffffffu, (wC & kFlagOwner) != 0);
-        const int64_t sl = (int64_t)orun + __popc(om & ((1u << lane) - 1u));
-        orun += __popc(om);
-        if (kk < dend) {
-          const HalfEdgeRec recC = {s_tmx[sc][lane], s_tmy[sc][lane], s_thm[sc][lane]};
-          const double2 pxy = s_pxy[scp][lane];
-          const PoseRec poseC = {pxy.x, pxy.y, s_pth[scp][lane]};
-          process(wC, recC, poseC, sl);
-        }
-        sc = (sc + 1 == kDS) ? 0 : sc + 1;
-        scp = (scp + 1 == kGS) ? 0 : scp + 1;
-      }
-    }
-    cp_async_wait<0>();
-  }
-#endif
   if (has_row) {
     Hdiag[0 * L.ldn + lr] = d00; Hdiag[1 * L.ldn + lr] = d01; Hdiag[2 * L.ldn + lr] = d02;
     Hdiag[3 * L.ldn + lr] = d11; Hdiag[4 * L.ldn + lr] = d12; Hdiag[5 * L.ldn + lr] = d22;
