@@ -205,6 +205,50 @@ inline double cost_edge_double(const oracle_problem* p, const double* x, int k) 
   return 0.5 * rho[0];
 }
 
+// METHOD 2 (switchable constraints): loop edges (kind >= 1) carry a scalar switch s, e = s * e_plain
+// (ceres_error.cpp:238-297), Huber on that block; plus the prior row sqrt(lambda) (1 - s) without loss
+// (:300-317, main.cpp:105-150).  Corrected residual r[3], pose Jacobian J[18] (3x6), switch Jacobian Js[3].
+inline void eval_edge_jet_sc(const oracle_problem* p, const double* x, double s, int k,
+                             double* r, double* J, double* Js, double* cost) {
+  const int ia = p->edge_a[k], ib = p->edge_b[k];
+  const Meas q = make_meas(p->meas_xyt[3 * k], p->meas_xyt[3 * k + 1], p->meas_xyt[3 * k + 2]);
+  Jet P1[3], P2[3], d[3], ps;
+  for (int i = 0; i < 3; ++i) { P1[i] = Jet(x[3 * ia + i], i); P2[i] = Jet(x[3 * ib + i], 3 + i); }
+  functor<Jet>(q, false, p->phi, P1, P2, d, &ps);
+  for (int i = 0; i < 3; ++i) {
+    r[i] = s * d[i].a;
+    for (int j = 0; j < 6; ++j) J[6 * i + j] = s * d[i].v[j] + 0.0 * d[i].a;
+    Js[i] = s * 0.0 + 1.0 * d[i].a;
+  }
+  const double sq = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  double rho[3];
+  Huber(p->huber_delta).eval(sq, rho);
+  *cost = 0.5 * rho[0];
+  const double sc = std::sqrt(rho[1]);
+  for (int i = 0; i < 18; ++i) J[i] *= sc;
+  for (int i = 0; i < 3; ++i) { r[i] *= sc; Js[i] *= sc; }
+}
+inline double cost_edge_double_sc(const oracle_problem* p, const double* x, double s, double lambda, int k) {
+  const int ia = p->edge_a[k], ib = p->edge_b[k];
+  const Meas q = make_meas(p->meas_xyt[3 * k], p->meas_xyt[3 * k + 1], p->meas_xyt[3 * k + 2]);
+  double e[3], ps;
+  functor<double>(q, false, p->phi, x + 3 * ia, x + 3 * ib, e, &ps);
+  double rho[3];
+  Huber(p->huber_delta).eval((s * e[0]) * (s * e[0]) + (s * e[1]) * (s * e[1]) + (s * e[2]) * (s * e[2]), rho);   // |s e|^2
+  const double pr = std::sqrt(lambda) * (1.0 - s);
+  return 0.5 * rho[0] + 0.5 * pr * pr;
+}
+
+// Per-loop-edge switch blocks of the normal equations (METHOD 2); empty for METHOD 0/1.
+struct SwitchBlocks {
+  bool on = false;
+  double lambda = 1.0;
+  std::vector<double> s;        // E switch values (entries of odometry edges unused)
+  std::vector<double> hss, gs;  // J_s^T J_s + lambda,  J_s^T r - lambda (1 - s)
+  std::vector<double> hps;      // E x 6: J_a^T J_s, J_b^T J_s
+  bool has(const oracle_problem* p, int k) const { return on && p->kind[k] != 0; }
+};
+
 int set_threads(const oracle_problem* p) {
   int t = p->num_threads > 0 ? p->num_threads : 1;
 #ifdef _OPENMP
@@ -281,13 +325,14 @@ void build_structure(const oracle_problem* p, Structure& S) {
 
 // H blocks (nb x 9) and gradient (N x 3) at x, plus the total cost.
 void assemble(const oracle_problem* p, const Structure& S, const double* x, double* Hv, double* g,
-              double* cost_out, std::vector<double>& Jbuf, std::vector<double>& rbuf) {
+              double* cost_out, std::vector<double>& Jbuf, std::vector<double>& rbuf, SwitchBlocks* W = nullptr) {
   const int E = S.E, N = S.N;
   const int nb = (int)S.col_idx.size();
   Jbuf.resize((size_t)E * 18);
   rbuf.resize((size_t)E * 3);
   double cost = 0.0;
-  const int nt = set_threads(p);
+  const int nt = (W && W->on) ? 1 : set_threads(p);
+  if (W && W->on) { W->hss.assign(E, 0.0); W->gs.assign(E, 0.0); W->hps.assign((size_t)E * 6, 0.0); }
   if (nt == 1) {
     // Serial, in residual-block order, like the reference's single-threaded Ceres.
     std::fill(Hv, Hv + (size_t)nb * 9, 0.0);
@@ -296,7 +341,18 @@ void assemble(const oracle_problem* p, const Structure& S, const double* x, doub
       double* J = &Jbuf[(size_t)k * 18];
       double* r = &rbuf[(size_t)k * 3];
       double psi, rho1, c;
-      eval_edge_jet(p, x, k, false, r, J, &psi, &rho1, &c);
+      if (W && W->has(p, k)) {
+        double Js[3];
+        const double sk = W->s[k];
+        eval_edge_jet_sc(p, x, sk, k, r, J, Js, &c);
+        const double pr = std::sqrt(W->lambda) * (1.0 - sk);          // prior residual, Jacobian -sqrt(lambda)
+        c += 0.5 * pr * pr;
+        W->hss[k] = Js[0] * Js[0] + Js[1] * Js[1] + Js[2] * Js[2] + W->lambda;
+        W->gs[k] = Js[0] * r[0] + Js[1] * r[1] + Js[2] * r[2] - std::sqrt(W->lambda) * pr;
+        for (int i = 0; i < 6; ++i) W->hps[(size_t)k * 6 + i] = J[i] * Js[0] + J[6 + i] * Js[1] + J[12 + i] * Js[2];
+      } else {
+        eval_edge_jet(p, x, k, false, r, J, &psi, &rho1, &c);
+      }
       cost += c;
       const int a = p->edge_a[k], b = p->edge_b[k];
       if (S.slot_aa[k] >= 0) {
@@ -722,8 +778,8 @@ int oracle_linear_solve(const oracle_problem* p, const double* pose_xyt, const d
   return 0;
 }
 
-int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* pose_xyt_inout,
-                 oracle_summary* sum, oracle_iteration* trace, int32_t trace_cap) {
+static int lm_impl(const oracle_problem* p, const oracle_lm_options* opt, double* pose_xyt_inout, double* switch_inout,
+                   double sc_lambda, oracle_summary* sum, oracle_iteration* trace, int32_t trace_cap) {
   if (!check_problem(p) || !opt || !pose_xyt_inout || !sum) return 1;
   std::memset(sum, 0, sizeof(*sum));
   const int N = p->n_poses;
@@ -734,6 +790,16 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
   C.symbolic(S);
   const int nb = (int)S.col_idx.size();
   const int n = C.n;
+  const int E = p->n_edges;
+  // METHOD 2: one switch per loop edge, eliminated edge by edge inside the linear solve (a switch couples only
+  // to the two poses of its edge, so the Schur complement onto the poses keeps the pose block pattern and is
+  // what a sparse Cholesky of the full system computes)
+  SwitchBlocks W;
+  W.on = switch_inout != nullptr;
+  W.lambda = sc_lambda;
+  if (W.on) W.s.assign(switch_inout, switch_inout + E);
+  std::vector<double> sw_c(W.s), sw_best(W.s), sw_scale(W.on ? E : 0, 1.0), sw_diag(W.on ? E : 0, 0.0), sw_step(W.on ? E : 0, 0.0);
+  std::vector<double> Hr;
 
   std::vector<double> x(pose_xyt_inout, pose_xyt_inout + (size_t)N * 3), xc(x), best(x);
   std::vector<double> Hv((size_t)nb * 9), g((size_t)N * 3), Jb, rb;
@@ -741,15 +807,23 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
   std::vector<double> Hs((size_t)nb * 9), dadd(n), b(n), step((size_t)N * 3, 0.0), delta((size_t)N * 3, 0.0);
   double eval_time = 0.0, solve_time = 0.0;
 
-  auto free_norm = [&](const std::vector<double>& v) {
+  auto free_norm = [&](const std::vector<double>& v, const std::vector<double>& sv) {
     double s = 0.0;
     for (int i = 0; i < N; ++i) if (S.is_free[i]) for (int c = 0; c < 3; ++c) s += v[3 * i + c] * v[3 * i + c];
+    for (int k = 0; k < E; ++k) if (W.has(p, k)) s += sv[k] * sv[k];
     return std::sqrt(s);
   };
   auto grad_norms = [&](double* gmax, double* gnorm) {
     double m = 0.0, s = 0.0;
     for (int i = 0; i < N; ++i) if (S.is_free[i]) for (int c = 0; c < 3; ++c) { m = std::max(m, std::fabs(g[3 * i + c])); s += g[3 * i + c] * g[3 * i + c]; }
+    for (int k = 0; k < E; ++k) if (W.has(p, k)) { m = std::max(m, std::fabs(W.gs[k])); s += W.gs[k] * W.gs[k]; }
     *gmax = m; *gnorm = std::sqrt(s);
+  };
+  auto cost_at = [&](const double* xx, const std::vector<double>& sv) {
+    if (!W.on) return total_cost(p, xx);
+    double c = 0.0;
+    for (int k = 0; k < E; ++k) c += W.has(p, k) ? cost_edge_double_sc(p, xx, sv[k], W.lambda, k) : cost_edge_double(p, xx, k);
+    return c;
   };
   auto hdiag = [&](int i, int c) { return Hv[(size_t)S.row_ptr[i] * 9 + 4 * c]; };  // diag block is first in its row
 
@@ -770,13 +844,16 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
 
   // --- iteration zero -----------------------------------------------------------------
   double x_cost = 0.0;
-  double x_norm = free_norm(x);
+  double x_norm = free_norm(x, W.s);
   double t0 = now_s();
-  assemble(p, S, x.data(), Hv.data(), g.data(), &x_cost, Jb, rb);
+  assemble(p, S, x.data(), Hv.data(), g.data(), &x_cost, Jb, rb, &W);
   eval_time += now_s() - t0;
   if (!std::isfinite(x_cost)) { sum->termination_type = 2; std::snprintf(sum->message, sizeof(sum->message), "Initial cost is not finite."); return 4; }
   if (opt->jacobi_scaling)
+  {
     for (int i = 0; i < N; ++i) if (S.is_free[i]) for (int c = 0; c < 3; ++c) scale[3 * i + c] = 1.0 / (1.0 + std::sqrt(hdiag(i, c)));
+    for (int k = 0; k < E; ++k) if (W.has(p, k)) sw_scale[k] = 1.0 / (1.0 + std::sqrt(W.hss[k]));
+  }
   oracle_iteration it;
   std::memset(&it, 0, sizeof(it));
   it.iteration = 0;
@@ -813,6 +890,9 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
         const double d = scale[3 * i + c] * scale[3 * i + c] * hdiag(i, c);   // colnorm^2 of the scaled J
         diagonal[3 * i + c] = std::min(std::max(d, opt->min_lm_diagonal), opt->max_lm_diagonal);
       }
+    if (!reuse_diagonal)
+      for (int k = 0; k < E; ++k) if (W.has(p, k))
+        sw_diag[k] = std::min(std::max(sw_scale[k] * sw_scale[k] * W.hss[k], opt->min_lm_diagonal), opt->max_lm_diagonal);
     t0 = now_s();
     // scaled normal equations: Hs = S H S, rhs = S g, D^2 = diagonal / radius
     for (int i = 0; i < N; ++i)
@@ -829,7 +909,39 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
         b[3 * o + c] = scale[3 * i + c] * g[3 * i + c];
       }
     }
-    C.load(Hs.data(), dadd.data());
+    // METHOD 2: Schur complement of every switch onto its two poses (scaled variables)
+    const double* Hload = Hs.data();
+    std::vector<double> sw_den, sw_b, sw_u;
+    if (W.on) {
+      Hr = Hs;
+      sw_den.assign(E, 1.0); sw_b.assign(E, 0.0); sw_u.assign((size_t)E * 6, 0.0);
+      for (int k = 0; k < E; ++k) if (W.has(p, k)) {
+        const int ia = p->edge_a[k], ib = p->edge_b[k];
+        const double sg_ = sw_scale[k];
+        const double den = sg_ * sg_ * W.hss[k] + sw_diag[k] / radius;
+        double* u = &sw_u[(size_t)k * 6];
+        for (int c = 0; c < 3; ++c) { u[c] = W.hps[(size_t)k * 6 + c] * scale[3 * ia + c] * sg_; u[3 + c] = W.hps[(size_t)k * 6 + 3 + c] * scale[3 * ib + c] * sg_; }
+        const double bs = sg_ * W.gs[k];
+        sw_den[k] = den; sw_b[k] = bs;
+        if (S.slot_aa[k] >= 0) {
+          double* H = &Hr[(size_t)S.slot_aa[k] * 9];
+          const int o = C.pose_to_ord[ia];
+          for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) H[3 * r + c] -= u[r] * u[c] / den; b[3 * o + r] -= u[r] * bs / den; }
+        }
+        if (S.slot_bb[k] >= 0) {
+          double* H = &Hr[(size_t)S.slot_bb[k] * 9];
+          const int o = C.pose_to_ord[ib];
+          for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) H[3 * r + c] -= u[3 + r] * u[3 + c] / den; b[3 * o + r] -= u[3 + r] * bs / den; }
+        }
+        if (S.slot_ab[k] >= 0) {
+          double* H = &Hr[(size_t)S.slot_ab[k] * 9];
+          const int oa = S.ab_transposed[k] ? 3 : 0, ob = S.ab_transposed[k] ? 0 : 3;
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[3 * r + c] -= u[oa + r] * u[ob + c] / den;
+        }
+      }
+      Hload = Hr.data();
+    }
+    C.load(Hload, dadd.data());
     bool ok = C.factor();
     if (ok) C.solve(b.data());
     reuse_diagonal = true;
@@ -840,6 +952,14 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
     if (ok) {
       std::fill(step.begin(), step.end(), 0.0);
       for (int o = 0; o < n / 3; ++o) { const int i = C.ord_to_pose[o]; for (int c = 0; c < 3; ++c) step[3 * i + c] = -b[3 * o + c]; }
+      // back-substitution of the switches: y_s = (b_s - u^T y_p) / den, step = -y
+      for (int k = 0; k < E; ++k) if (W.has(p, k)) {
+        const int ia = p->edge_a[k], ib = p->edge_b[k];
+        const double* u = &sw_u[(size_t)k * 6];
+        double uy = 0.0;   // u^T y_p = -u^T step_p   (constant poses have step 0)
+        for (int c = 0; c < 3; ++c) uy -= u[c] * step[3 * ia + c] + u[3 + c] * step[3 * ib + c];
+        sw_step[k] = -(sw_b[k] - uy) / sw_den[k];
+      }
       // model_cost_change = -(J step)^T (r + J step / 2) = -step^T (S g) - step^T Hs step / 2
       double sg = 0.0, shs = 0.0;
       for (int i = 0; i < N; ++i) if (S.is_free[i]) for (int c = 0; c < 3; ++c) sg += step[3 * i + c] * scale[3 * i + c] * g[3 * i + c];
@@ -850,6 +970,14 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
           for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc += step[3 * i + r] * Hs[(size_t)q * 9 + 3 * r + c] * step[3 * j + c];
           shs += (i == j) ? acc : 2.0 * acc;
         }
+      for (int k = 0; k < E; ++k) if (W.has(p, k)) {
+        const int ia = p->edge_a[k], ib = p->edge_b[k];
+        const double* u = &sw_u[(size_t)k * 6];
+        double us = 0.0;
+        for (int c = 0; c < 3; ++c) us += u[c] * step[3 * ia + c] + u[3 + c] * step[3 * ib + c];
+        sg += sw_step[k] * sw_b[k];
+        shs += sw_scale[k] * sw_scale[k] * W.hss[k] * sw_step[k] * sw_step[k] + 2.0 * sw_step[k] * us;
+      }
       model_cost_change = -sg - 0.5 * shs;
       it.step_is_valid = model_cost_change > 0.0;
     }
@@ -868,13 +996,16 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
     invalid = 0;
     for (size_t i = 0; i < delta.size(); ++i) delta[i] = step[i] * scale[i];
     for (size_t i = 0; i < xc.size(); ++i) xc[i] = x[i] + delta[i];
+    for (int k = 0; k < E; ++k) if (W.has(p, k)) sw_c[k] = W.s[k] + sw_step[k] * sw_scale[k];
     t0 = now_s();
-    double cand = total_cost(p, xc.data());
+    double cand = cost_at(xc.data(), sw_c);
     eval_time += now_s() - t0;
     if (!std::isfinite(cand)) cand = std::numeric_limits<double>::max();
 
     // ParameterToleranceReached
-    { double s = 0.0; for (int i = 0; i < N; ++i) if (S.is_free[i]) for (int c = 0; c < 3; ++c) { const double d = x[3 * i + c] - xc[3 * i + c]; s += d * d; } it.step_norm = std::sqrt(s); }
+    { double s = 0.0; for (int i = 0; i < N; ++i) if (S.is_free[i]) for (int c = 0; c < 3; ++c) { const double d = x[3 * i + c] - xc[3 * i + c]; s += d * d; }
+      for (int k = 0; k < E; ++k) if (W.has(p, k)) { const double d = W.s[k] - sw_c[k]; s += d * d; }
+      it.step_norm = std::sqrt(s); }
     it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
     const double step_size_tolerance = opt->parameter_tolerance * (x_norm + opt->parameter_tolerance);
     if (it.step_norm <= step_size_tolerance) {
@@ -897,9 +1028,10 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
     if (it.relative_decrease > opt->min_relative_decrease) {
       // HandleSuccessfulStep
       x = xc;
-      x_norm = free_norm(x);
+      if (W.on) W.s = sw_c;
+      x_norm = free_norm(x, W.s);
       t0 = now_s();
-      assemble(p, S, x.data(), Hv.data(), g.data(), &x_cost, Jb, rb);
+      assemble(p, S, x.data(), Hv.data(), g.data(), &x_cost, Jb, rb, &W);
       eval_time += now_s() - t0;
       it.step_is_successful = 1;
       it.cost = x_cost;
@@ -909,7 +1041,7 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
       decrease_factor = 2.0;
       reuse_diagonal = false;
       sum->num_successful_steps++;
-      if (x_cost < minimum_cost) { minimum_cost = x_cost; best = x; }
+      if (x_cost < minimum_cost) { minimum_cost = x_cost; best = x; sw_best = W.s; }
     } else {
       it.step_is_successful = 0;
       it.cost = cand;
@@ -925,6 +1057,7 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
   // Solver::Summary: user parameters hold the best accepted iterate; final_cost is the
   // minimum logged cost (Ceres SetSummaryFinalCost).
   std::copy(best.begin(), best.end(), pose_xyt_inout);
+  if (W.on) std::copy(sw_best.begin(), sw_best.end(), switch_inout);
   sum->final_cost = std::min(sum->initial_cost, min_logged_cost);
   sum->num_iterations = n_logged;
   sum->termination_type = term;
@@ -933,6 +1066,20 @@ int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* 
   sum->linear_solver_time_s = solve_time;
   std::snprintf(sum->message, sizeof(sum->message), "%s", msg);
   return 0;
+}
+
+
+int oracle_solve(const oracle_problem* p, const oracle_lm_options* opt, double* pose_xyt_inout,
+                 oracle_summary* sum, oracle_iteration* trace, int32_t trace_cap) {
+  return lm_impl(p, opt, pose_xyt_inout, nullptr, 1.0, sum, trace, trace_cap);
+}
+
+// METHOD 2 (main.cpp:105-150 with SC_ON): switches[E] in/out (entries of odometry edges are ignored; the
+// reference starts every switch at 1), prior weight lambda (1.0 in the reference).  p->dcs_on must be 0.
+int oracle_sc_solve(const oracle_problem* p, double lambda, const oracle_lm_options* opt, double* pose_xyt_inout,
+                    double* switches_inout, oracle_summary* sum, oracle_iteration* trace, int32_t trace_cap) {
+  if (!p || p->dcs_on || !switches_inout) return 1;
+  return lm_impl(p, opt, pose_xyt_inout, switches_inout, lambda, sum, trace, trace_cap);
 }
 
 }  // extern "C"

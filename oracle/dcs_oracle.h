@@ -103,6 +103,14 @@ int oracle_linear_solve(const oracle_problem* p, const double* pose_xyt, const d
 int oracle_solve(const oracle_problem* p, const oracle_lm_options* o, double* pose_xyt_inout,
                  oracle_summary* s, oracle_iteration* trace, int32_t trace_cap);
 
+/* METHOD 2 (switchable constraints, main.cpp:105-150 with SC_ON): Ceres-default LM over poses and one switch per
+ * loop edge.  The switches are eliminated edge by edge inside the linear solve (exact Schur complement).
+ * switches_inout[E]: entries of odometry edges are ignored; the reference starts every switch at 1.0, lambda = 1.0.
+ * p->dcs_on must be 0.  PARITY: functors pinned (oracle_sc_edge), minimiser unpinned like oracle_solve; the
+ * elimination is cross-checked against a dense full-system LM in tests/test_oracle_cpu.py. */
+int oracle_sc_solve(const oracle_problem* p, double lambda, const oracle_lm_options* o, double* pose_xyt_inout,
+                    double* switches_inout, oracle_summary* s, oracle_iteration* trace, int32_t trace_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,26 @@ class Oracle:
         return x, s, [trace[i] for i in range(min(cap, s.num_iterations))]
 
 
+def _sc_solve(self, switches=None, lam=1.0, pose_xyt=None, verbose=False, **opts):
+    """METHOD 2: LM over poses + one switch per loop edge (oracle_sc_solve). Returns x, switches[E], summary, trace."""
+    x = np.array(self.g.pose_xyt if pose_xyt is None else pose_xyt, dtype=np.float64, order="C")
+    sw = np.ones(self.g.n_edges) if switches is None else np.array(switches, dtype=np.float64, order="C")
+    o = LmOptions()
+    self.L.oracle_lm_options_default(C.byref(o))
+    o.verbose = 1 if verbose else 0
+    for k, v in opts.items():
+        setattr(o, k, v)
+    s = OSummary()
+    cap = o.max_num_iterations + 2
+    trace = (OIteration * cap)()
+    rc = self.L.oracle_sc_solve(C.byref(self.p), C.c_double(lam), C.byref(o), _ptr(x), _ptr(sw), C.byref(s), trace, cap)
+    assert rc == 0, rc
+    return x, sw, s, [trace[i] for i in range(min(cap, s.num_iterations))]
+
+
+Oracle.sc_solve = _sc_solve
+
+
 def closed_form_edge(pa, pb, meas, dcs, phi=0.5):
     pa = np.ascontiguousarray(pa, dtype=np.float64); pb = np.ascontiguousarray(pb, dtype=np.float64)
     meas = np.ascontiguousarray(meas, dtype=np.float64)

@@ -61,6 +61,22 @@ def solve_case(name, n_bogus):
     g.save_npz(f"{OUT}/{name}_{n_bogus}_seed1.npz", **extra)
 
 
+def method2():
+    """METHOD 2 (switchable constraints) LM traces of the oracle on the committed graphs -> method2_traces.npz.
+    Fixture for the GPU path of SURVEY section 8(f) N2; needs only the committed *_seed1.npz files."""
+    out = {}
+    for name in ("INTEL_50_seed1", "M3500_100_seed1"):
+        g = Graph.load_npz(f"{OUT}/{name}.npz")
+        x, sw, s, tr = O.Oracle(g, dcs_on=False).sc_solve(lam=1.0)
+        for k, v in trace_arrays(tr).items():
+            out[f"{name}_trace_{k}"] = v
+        out[f"{name}_final_cost"] = s.final_cost
+        out[f"{name}_final_pose"] = x
+        out[f"{name}_switches"] = sw
+        print(name, "METHOD 2", s.initial_cost, "->", s.final_cost, "iters", s.num_iterations, "ok", s.num_successful_steps)
+    np.savez_compressed(f"{OUT}/method2_traces.npz", **out)
+
+
 def structure():
     out = {}
     for name in ("CSAIL", "FR079", "FRH", "INTEL", "M3500", "MIT"):
@@ -81,8 +97,12 @@ def structure():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "method2":     # only the METHOD 2 traces (no reference checkout needed)
+        method2()
+        sys.exit(0)
     assert O.ref_lib() is not None, "build oracle/_ref first (make -C oracle ref)"
     structure()
     solve_case("INTEL", 50)
     solve_case("INTEL", 0)
     solve_case("M3500", 100)
+    method2()

@@ -215,3 +215,147 @@ def test_switchable_constraint_functors_match_reference():
     if O.ref_lib() is not None:
         assert checked == 400
 
+
+
+def _dense_sc_lm(g, lam, max_it, huber=0.01):
+    """Independent dense restatement of Ceres' default trust-region LM for METHOD 2: full Jacobian over
+    (free poses, switches), Jacobi scaling, LM diagonal, dense solve.  Returns the per-iteration costs, the
+    success flags, poses and switches."""
+    N, E = g.n_poses, g.n_edges
+    free = np.ones(N, bool); free[0] = False
+    pidx = -np.ones(N, int); pidx[free] = np.arange(free.sum())
+    loops = np.flatnonzero(g.kind != 0)
+    sidx = {int(k): 3 * int(free.sum()) + i for i, k in enumerate(loops)}
+    n = 3 * int(free.sum()) + len(loops)
+    b2 = huber * huber
+
+    def rho(sq):
+        if sq > b2:
+            r = np.sqrt(sq)
+            return 2 * huber * r - b2, max(np.finfo(float).tiny, huber / r)
+        return sq, 1.0
+
+    def lin(x, sw):
+        rows, r = [], []
+        cost = 0.0
+        for k in range(E):
+            a, b = int(g.edge_a[k]), int(g.edge_b[k])
+            s = sw[k] if g.kind[k] else 1.0
+            e, J = O.sc_edge(x[a], x[b], g.meas_xyt[k], s)
+            r0, r1 = rho(float(e @ e))
+            cost += 0.5 * r0
+            w = np.sqrt(r1)
+            Jr = np.zeros((3, n))
+            if free[a]: Jr[:, 3 * pidx[a]:3 * pidx[a] + 3] = w * J[:, 0:3]
+            if free[b]: Jr[:, 3 * pidx[b]:3 * pidx[b] + 3] = w * J[:, 3:6]
+            if g.kind[k]: Jr[:, sidx[k]] = w * J[:, 6]
+            rows.append(Jr); r.append(w * e)
+            if g.kind[k]:
+                pr = np.sqrt(lam) * (1.0 - s)
+                Jp = np.zeros((1, n)); Jp[0, sidx[k]] = -np.sqrt(lam)
+                rows.append(Jp); r.append(np.array([pr])); cost += 0.5 * pr * pr
+        return np.vstack(rows), np.concatenate(r), cost
+
+    def cost_only(x, sw):
+        c = 0.0
+        for k in range(E):
+            s = sw[k] if g.kind[k] else 1.0
+            e, _ = O.sc_edge(x[int(g.edge_a[k])], x[int(g.edge_b[k])], g.meas_xyt[k], s)
+            c += 0.5 * rho(float(e @ e))[0]
+            if g.kind[k]: c += 0.5 * lam * (1.0 - s) ** 2
+        return c
+
+    def pack(x, sw): return np.concatenate([x[free].ravel(), sw[loops]])
+
+    def unpack(v, x, sw):
+        x = x.copy(); sw = sw.copy()
+        x[free] = v[:3 * free.sum()].reshape(-1, 3); sw[loops] = v[3 * free.sum():]
+        return x, sw
+
+    x, sw = g.pose_xyt.copy(), np.ones(E)
+    J, r, cost = lin(x, sw)
+    scale = 1.0 / (1.0 + np.sqrt((J * J).sum(0)))
+    radius, dec, reuse, diag = 1e4, 2.0, False, None
+    costs, flags = [cost], []
+    for it in range(max_it):
+        Js = J * scale
+        if not reuse: diag = np.clip((Js * Js).sum(0), 1e-6, 1e32)
+        A = Js.T @ Js
+        y = np.linalg.solve(A + np.diag(diag / radius), Js.T @ r)
+        step = -y
+        mcc = -(step @ (Js.T @ r)) - 0.5 * step @ A @ step
+        reuse = True
+        assert mcc > 0
+        v = pack(x, sw) + step * scale
+        xc, swc = unpack(v, x, sw)
+        cand = cost_only(xc, swc)
+        rel = (cost - cand) / mcc
+        if rel > 1e-3:
+            x, sw = xc, swc
+            J, r, cost = lin(x, sw)
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rel - 1.0) ** 3)); dec = 2.0; reuse = False
+            costs.append(cost); flags.append(1)
+        else:
+            radius /= dec; dec *= 2.0
+            costs.append(cand); flags.append(0)
+    return costs, flags, x, sw
+
+
+def test_switchable_constraints_lm_elimination_matches_dense_full_system():
+    """METHOD 2 groundwork: the oracle eliminates every switch inside the linear solve; an independent dense LM
+    over the full (poses + switches) system must give the same iterates."""
+    rng = np.random.default_rng(21)
+    N = 40
+    th = np.cumsum(rng.normal(0, 0.1, N)); xy = np.cumsum(np.c_[np.cos(th), np.sin(th)], axis=0)
+    gt = np.c_[xy, th]
+    ea = list(range(N - 1)); eb = list(range(1, N)); kind = [0] * (N - 1)
+    for _ in range(25):
+        a, b = sorted(rng.choice(N, 2, replace=False))
+        if b - a > 5: ea.append(int(a)); eb.append(int(b)); kind.append(1 if rng.random() < 0.7 else 2)
+    E = len(ea)
+    meas = np.zeros((E, 3))
+    for k in range(E):
+        pa, pb = gt[ea[k]], gt[eb[k]]
+        c, s = np.cos(pa[2]), np.sin(pa[2])
+        d = pb[:2] - pa[:2]
+        meas[k] = [c * d[0] + s * d[1], -s * d[0] + c * d[1], pb[2] - pa[2]]
+        if kind[k] == 2: meas[k] = 0.0                          # bogus loops, like add_random_C
+    meas += rng.normal(0, 0.01, meas.shape)
+    pose = gt + rng.normal(0, 0.05, gt.shape); pose[0] = gt[0]
+    import dcs_b200 as D
+    g = D.Graph(pose, ea, eb, meas, kind)
+    its = 12
+    costs, flags, xd, swd = _dense_sc_lm(g, 1.0, its)
+    ora = O.Oracle(g, dcs_on=False)
+    x, sw, summ, trace = ora.sc_solve(lam=1.0, max_num_iterations=its, function_tolerance=0.0, parameter_tolerance=0.0,
+                                      gradient_tolerance=0.0)
+    got = [t.cost for t in trace]
+    assert len(got) == its + 1
+    assert [t.step_is_successful for t in trace[1:]] == flags
+    assert np.allclose(got, costs, rtol=1e-9, atol=1e-14)
+    loops = np.flatnonzero(np.array(kind) != 0)
+    assert np.abs(sw[loops] - swd[loops]).max() < 1e-7 and np.abs(x - xd).max() < 1e-7
+    # Huber(0.01) on the switched block leaves the switches a weak pull (rho' = 0.01 / |s e|): the bogus loops move
+    # away from 1, the consistent ones stay there
+    bog = np.flatnonzero(np.array(kind) == 2); good = np.flatnonzero(np.array(kind) == 1)
+    if len(bog): assert sw[bog].mean() < sw[good].mean() - 0.05
+    assert sw[good].min() > 0.9
+
+
+@pytest.mark.parametrize("name", ["INTEL_50_seed1", "M3500_100_seed1"])
+def test_method2_lm_trace_reproduces_golden(name):
+    """METHOD 2 fixture for the GPU path to come (tests/golden/method2_traces.npz, made by make_golden.py method2):
+    the oracle must reproduce it exactly."""
+    z = np.load(os.path.join(GOLDEN, "method2_traces.npz"))
+    g, _ = load_case(name)
+    x, sw, s, tr = O.Oracle(g, dcs_on=False).sc_solve(lam=1.0)
+    assert np.allclose([t.cost for t in tr], z[f"{name}_trace_cost"], rtol=1e-12)
+    assert np.array_equal([t.step_is_successful for t in tr], z[f"{name}_trace_ok"])
+    assert np.isclose(s.final_cost, float(z[f"{name}_final_cost"]), rtol=1e-12)
+    loops = g.kind != 0
+    assert np.allclose(sw[loops], z[f"{name}_switches"][loops], rtol=0, atol=1e-12)
+    assert np.all(sw[~loops] == 1.0)                                     # odometry edges have no switch
+    # METHOD 2 starts from the METHOD 0 cost (all switches 1) and ends below METHOD 0's final cost
+    g0, z0 = load_case(name)
+    assert np.isclose(tr[0].cost, float(z0["cost_init_dcs0"]), rtol=1e-12)
+    assert s.final_cost < float(z0["final_cost_dcs0"])
