@@ -247,7 +247,7 @@ def main():
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "n_poses": n_poses, "n_edges": g.n_edges, "partition": f"pose-range x{world}",
-                   "l2": "inputs larger than L2 (352 MB half-edge stream + 0.7 GB block output per launch)",
+                   "l2": "inputs larger than L2 (224 MB half-edge stream read + 0.38 GB of blocks, diagonals and gradient written per launch)",
                    "create_s": t_create},
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / a.steps},
