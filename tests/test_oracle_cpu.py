@@ -359,3 +359,71 @@ def test_method2_lm_trace_reproduces_golden(name):
     g0, z0 = load_case(name)
     assert np.isclose(tr[0].cost, float(z0["cost_init_dcs0"]), rtol=1e-12)
     assert s.final_cost < float(z0["final_cost_dcs0"])
+
+
+@pytest.mark.parametrize("dcs", [0, 1])
+def test_lm_matches_dense_restatement(dcs):
+    """Second, independent restatement of the minimiser (dense numpy: full Jacobian, Jacobi scaling, LM diagonal,
+    dense solve, Ceres' accept / radius rules) against the oracle's sparse-Cholesky LM, METHOD 0 and 1, on a graph
+    small enough for dense algebra.  (Ceres itself is absent offline; this pins the oracle's linear algebra and
+    bookkeeping to a second implementation, not to Ceres.)"""
+    rng = np.random.default_rng(33 + dcs)
+    N = 60
+    th = np.cumsum(rng.normal(0, 0.15, N)); xy = np.cumsum(np.c_[np.cos(th), np.sin(th)], axis=0)
+    gt = np.c_[xy, th]
+    ea = list(range(N - 1)); eb = list(range(1, N)); kind = [0] * (N - 1)
+    while len(ea) < N - 1 + 40:
+        a, b = sorted(int(v) for v in rng.choice(N, 2, replace=False))
+        if b - a > 5: ea.append(a); eb.append(b); kind.append(1 if rng.random() < 0.75 else 2)
+    E = len(ea)
+    meas = np.zeros((E, 3))
+    for k in range(E):
+        pa, pb = gt[ea[k]], gt[eb[k]]
+        c, s = np.cos(pa[2]), np.sin(pa[2]); d = pb[:2] - pa[:2]
+        meas[k] = [c * d[0] + s * d[1], -s * d[0] + c * d[1], pb[2] - pa[2]]
+        if kind[k] == 2: meas[k] = 0.0
+    meas += rng.normal(0, 0.02, meas.shape)
+    pose = gt + rng.normal(0, 0.1, gt.shape); pose[0] = gt[0]
+    import dcs_b200 as D
+    g = D.Graph(pose, ea, eb, meas, kind)
+    ora = O.Oracle(g, dcs_on=bool(dcs))
+    free = np.ones(N, bool); free[0] = False
+    col = -np.ones(N, int); col[free] = 3 * np.arange(free.sum())
+    n = 3 * int(free.sum())
+
+    def lin(x):
+        ev = ora.evaluate(x)                          # corrected residuals / Jacobians per edge
+        J = np.zeros((3 * E, n))
+        for k in range(E):
+            a, b = ea[k], eb[k]
+            if free[a]: J[3 * k:3 * k + 3, col[a]:col[a] + 3] = ev["jacobians"][k][:, 0:3]
+            if free[b]: J[3 * k:3 * k + 3, col[b]:col[b] + 3] = ev["jacobians"][k][:, 3:6]
+        return J, ev["residuals"].ravel(), ev["cost"]
+
+    its = 15
+    x = g.pose_xyt.copy()
+    J, r, cost = lin(x)
+    scale = 1.0 / (1.0 + np.sqrt((J * J).sum(0)))
+    radius, dec, reuse, diag = 1e4, 2.0, False, None
+    costs, flags = [cost], []
+    for _ in range(its):
+        Js = J * scale
+        if not reuse: diag = np.clip((Js * Js).sum(0), 1e-6, 1e32)
+        A = Js.T @ Js
+        step = -np.linalg.solve(A + np.diag(diag / radius), Js.T @ r)
+        mcc = -(step @ (Js.T @ r)) - 0.5 * step @ A @ step
+        reuse = True
+        xc = x.copy(); xc[free] += (step * scale).reshape(-1, 3)
+        cand = ora.cost(xc)
+        rel = (cost - cand) / mcc
+        if rel > 1e-3:
+            x = xc; J, r, cost = lin(x)
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rel - 1.0) ** 3)); dec = 2.0; reuse = False
+            costs.append(cost); flags.append(1)
+        else:
+            radius /= dec; dec *= 2.0
+            costs.append(cand); flags.append(0)
+    xo, s, tr = ora.solve(max_num_iterations=its, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    assert [t.step_is_successful for t in tr[1:]] == flags
+    assert np.allclose([t.cost for t in tr], costs, rtol=1e-9, atol=1e-14)
+    assert sum(flags) >= 5
