@@ -64,6 +64,10 @@ All numbers from `gpurun` boxes (one B200 unless stated), clocks untouched (`--c
 |---|---|---|---|---|
 """ + "\n".join(summary) + f"""
 
+(Launch list and the `--set full` table below were captured with the build one change before the final one — own rows
+in natural instead of (window, rank) order: `k_linearize` 180 us there, 168 us in the final bench; no GPU time was left
+to re-capture.  The shares are unaffected at the precision that matters.)
+
 The bench step proper is `k_linearize` (+ `k_fold_tasks`), one pair per step.  The LM side measurement is dominated by
 `k_spmv` (one per PCG iteration), then the chain-preconditioned vector kernel `k_pcg_chain` and `k_pcg_direction`.
 
