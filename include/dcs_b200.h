@@ -91,7 +91,12 @@ typedef struct dcs_options {
   /* execution */
   int32_t device;                 /* CUDA device ordinal                                 */
   int32_t verbose;                /* 1: Ceres-style progress table on stdout             */
-  /* multi-GPU: one process per GPU. world==1 -> single device.                           */
+  /* multi-GPU: one process per GPU. world==1 -> single device.
+   * With world > 1 every call that takes or returns poses (dcs_create, dcs_evaluate, dcs_linearize, dcs_cost,
+   * dcs_solve) is COLLECTIVE: all ranks make the same calls in the same order with the same full-size arrays;
+   * a rank reads only its own pose rows (dcs_partition) from the input and receives its halo from the owners
+   * over NVLink (peer-memory push; DCS_HALO=nccl forces grouped ncclSend/ncclRecv), outputs are complete on
+   * every rank.                                                                           */
   int32_t rank;
   int32_t world;
   const void* nccl_unique_id;     /* 128-byte ncclUniqueId shared by all ranks           */
