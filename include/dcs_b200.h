@@ -28,6 +28,13 @@
 
 #include <stdint.h>
 
+/* The library is built with -fvisibility=hidden: exactly the entry points declared here are exported. */
+#if defined(__GNUC__)
+#define DCS_API __attribute__((visibility("default")))
+#else
+#define DCS_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -60,7 +67,7 @@ typedef struct dcs_graph {
   const int32_t* edge_b;    /* second endpoint (Edge::b->index)                          */
   const double* meas_xyt;   /* n_edges x 3 (Edge::x, y, theta)                           */
   const uint8_t* kind;      /* DCS_EDGE_*; order = odometry, closure, bogus (main.cpp)   */
-  int32_t fixed_pose;       /* parameter block held constant (main.cpp:153 -> 0)         */
+  int32_t fixed_pose;       /* parameter block held constant (main.cpp:153 -> 0); -1: none */
 } dcs_graph;
 
 typedef struct dcs_options {
@@ -81,7 +88,7 @@ typedef struct dcs_options {
   double parameter_tolerance;         /* 1e-8                                            */
   int32_t max_num_consecutive_invalid_steps; /* 5                                        */
   int32_t jacobi_scaling;             /* 1                                               */
-  /* linear solver: block-Jacobi PCG on the 3x3-block normal equations                    */
+  /* linear solver: preconditioned CG on the 3x3-block normal equations (see `preconditioner`) */
   double pcg_rel_tol;             /* stop when |r|_2 <= pcg_rel_tol * |rhs|_2            */
   int32_t pcg_max_iter;
   int32_t pcg_check_every;        /* iterations per graph launch between host checks     */
@@ -91,12 +98,14 @@ typedef struct dcs_options {
   /* execution */
   int32_t device;                 /* CUDA device ordinal                                 */
   int32_t verbose;                /* 1: Ceres-style progress table on stdout             */
-  /* multi-GPU: one process per GPU. world==1 -> single device.
+  /* multi-GPU: one process per GPU (world <= 8: the GPUs of one NVSwitch node). world==1 -> single device.
    * With world > 1 every call that takes or returns poses (dcs_create, dcs_evaluate, dcs_linearize, dcs_cost,
    * dcs_solve) is COLLECTIVE: all ranks make the same calls in the same order with the same full-size arrays;
    * a rank reads only its own pose rows (dcs_partition) from the input and receives its halo from the owners
-   * over NVLink (peer-memory push; DCS_HALO=nccl forces grouped ncclSend/ncclRecv), outputs are complete on
-   * every rank.                                                                           */
+   * over NVLink (peer-memory push; DCS_HALO=nccl forces grouped ncclSend/ncclRecv).  Outputs: scalars (cost,
+   * summaries, traces) and the poses written by dcs_solve are complete and identical on every rank; per-row
+   * vector outputs (the gradient of dcs_evaluate / dcs_linearize, w of dcs_pcg_solve) are filled for the
+   * calling rank's own rows only and zero elsewhere (sum over ranks = the full vector).              */
   int32_t rank;
   int32_t world;
   const void* nccl_unique_id;     /* 128-byte ncclUniqueId shared by all ranks           */
@@ -122,7 +131,8 @@ typedef struct dcs_iteration {
 typedef struct dcs_summary {
   double initial_cost;
   double final_cost;
-  int32_t num_iterations;         /* entries written to the trace (iteration 0 included) */
+  int32_t num_iterations;         /* entries written to the trace (iteration 0 included; as in Ceres, the iteration
+                                   * that ends on the parameter / function tolerance is not appended)          */
   int32_t num_successful_steps;
   int32_t num_unsuccessful_steps;
   int32_t termination_type;       /* DCS_CONVERGENCE / DCS_NO_CONVERGENCE / DCS_FAILURE  */
@@ -136,73 +146,73 @@ typedef struct dcs_summary {
 typedef struct dcs_handle dcs_handle;
 
 /* Fill o with the reference's defaults (see field comments). */
-void dcs_options_default(dcs_options* o);
+DCS_API void dcs_options_default(dcs_options* o);
 
 /* Library / device probes (no compute). */
-const char* dcs_version(void);
-int dcs_device_count(void);
+DCS_API const char* dcs_version(void);
+DCS_API int dcs_device_count(void);
 
 /* Pose-range / edge-slice partition a handle with (rank, world) uses: contiguous, equal-sized pose ranges
  * following the odometry chain (padded to the kernel's row window), equal edge slices for the cost-only
  * kernel.  Pure host arithmetic (no CUDA): out = {row_lo, n_rows, rows_per_rank, edge_lo, edge_hi}. */
-int dcs_partition(int32_t n_poses, int32_t n_edges, int32_t rank, int32_t world, int32_t out[5]);
+DCS_API int dcs_partition(int32_t n_poses, int32_t n_edges, int32_t rank, int32_t world, int32_t out[5]);
 
 /* 128-byte id for a multi-rank group; rank 0 calls it and ships the bytes to the peers. */
-int dcs_nccl_unique_id(void* out128);
+DCS_API int dcs_nccl_unique_id(void* out128);
 
 /* Upload the graph, build the half-edge CSR and the block pattern (one-time sort). */
-int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out);
-void dcs_destroy(dcs_handle* h);
+DCS_API int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out);
+DCS_API void dcs_destroy(dcs_handle* h);
 
 /* Parity hook: evaluate at pose_xyt (NULL -> the handle's current poses).
  * Any output pointer may be NULL.  Shapes: residuals E x 3, jacobians E x 18
  * (row-major 3x6 per edge: d e / d(pa, pb), after DCS and the Huber corrector),
  * psi E, rho1 E (Huber rho'), gradient N x 3 (zeros at the fixed pose). */
-int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost,
+DCS_API int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost,
                  double* residuals, double* jacobians, double* psi, double* rho1,
                  double* gradient);
 
 /* Hot path on host buffers: H2D poses, fused eval + J^T J / J^T r assembly on device,
  * D2H cost and gradient (either may be NULL).  The assembled H stays on the device. */
-int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* gradient);
+DCS_API int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* gradient);
 
 /* Same launches with everything resident on the device (used by bench.py's `value`). */
-int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total);
+DCS_API int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total);
 
 /* Cost-only evaluation (candidate point inside LM). */
-int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost);
+DCS_API int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost);
 
 /* Integer parity hook: upper block pattern of J^T J over the non-constant poses,
  * {(i,i)} U {(min(a,b),max(a,b))}, as CSR over poses.  Call with NULL arrays to get
  * the sizes; then with row_ptr[n_poses+1] and col_idx[nnzb]. */
-int dcs_get_pattern(dcs_handle* h, int32_t* n_block_rows, int32_t* nnzb,
+DCS_API int dcs_get_pattern(dcs_handle* h, int32_t* n_block_rows, int32_t* nnzb,
                     int32_t* row_ptr, int32_t* col_idx);
 
 /* Values of the assembled J^T J on that pattern (nnzb x 9, row-major 3x3), from the last
  * dcs_linearize / dcs_evaluate / accepted LM step. */
-int dcs_get_hessian(dcs_handle* h, double* block_values);
+DCS_API int dcs_get_hessian(dcs_handle* h, double* block_values);
 
 /* One linear solve (H + diag(lambda)) w = rhs with block-Jacobi PCG on the current H.
  * lambda, rhs, w: N x 3 host arrays (entries of the fixed pose ignored / zero). */
-int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double* w,
+DCS_API int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs, double* w,
                   int32_t* iterations, double* rel_residual);
 
 /* Full DCS-LM solve. pose_xyt_inout: N x 3, updated in place (Node::p write-back,
  * include/graph.h:10-17).  trace may be NULL; trace_cap entries are written at most. */
-int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* summary,
+DCS_API int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* summary,
               dcs_iteration* trace, int32_t trace_cap);
 
 /* Page-locked host buffers (cudaHostAlloc).  Pose / gradient arrays handed to dcs_linearize, dcs_evaluate and
  * dcs_solve may live anywhere; when they are page-locked the library DMAs straight from / into them instead of
  * staging through its own pinned bounce buffer. */
-void* dcs_host_alloc(uint64_t bytes);
-void dcs_host_free(void* p);
+DCS_API void* dcs_host_alloc(uint64_t bytes);
+DCS_API void dcs_host_free(void* p);
 
 /* Last CUDA / NCCL error text for this thread ("" if none). */
-const char* dcs_last_error(void);
+DCS_API const char* dcs_last_error(void);
 
 /* Number of kernel launches issued by this library since the counter was last reset. */
-int64_t dcs_launch_count(int reset);
+DCS_API int64_t dcs_launch_count(int reset);
 
 #ifdef __cplusplus
 }

@@ -1012,7 +1012,7 @@ static int lm_impl(const oracle_problem* p, const oracle_lm_options* opt, double
       term = 0; msg = "Parameter tolerance reached.";
       it.cost = x_cost; it.trust_region_radius = radius;
       it.iteration_time_s = now_s() - it_start; it.cumulative_time_s = now_s() - t_start;
-      log_iter(it); break;
+      break;   // Ceres returns from Minimize() here: the terminating iteration is not appended to summary.iterations
     }
     // FunctionToleranceReached
     it.cost_change = x_cost - cand;
@@ -1020,7 +1020,7 @@ static int lm_impl(const oracle_problem* p, const oracle_lm_options* opt, double
       term = 0; msg = "Function tolerance reached.";
       it.cost = x_cost; it.trust_region_radius = radius;
       it.iteration_time_s = now_s() - it_start; it.cumulative_time_s = now_s() - t_start;
-      log_iter(it); break;
+      break;   // Ceres returns from Minimize() here: the terminating iteration is not appended to summary.iterations
     }
     // IsStepSuccessful
     it.relative_decrease = (cand >= std::numeric_limits<double>::max()) ? std::numeric_limits<double>::lowest()

@@ -49,7 +49,7 @@ def test_reader_and_injection_match_reference(name, n_bogus, tmp_path):
     host.dcs_host_add_random_C(hh, n_bogus, 1, 1)
     mine_n, mine_e = str(tmp_path / "n.txt"), str(tmp_path / "e.txt")
     host.dcs_host_write_nodes(hh, mine_n.encode()); host.dcs_host_write_edges(hh, mine_e.encode())
-    host.dcs_host_free(hh)
+    host.dcs_host_graph_free(hh)
     ref_n, ref_e = str(tmp_path / "rn.txt"), str(tmp_path / "re.txt")
     L.ref_write.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     L.ref_write(h, ref_n.encode(), ref_e.encode())
@@ -114,7 +114,7 @@ def test_writer_format(tmp_path):
     h = host.dcs_host_parse_g2o(text.encode(), len(text))
     host.dcs_host_write_nodes(h, str(tmp_path / "n.txt").encode())
     host.dcs_host_write_edges(h, str(tmp_path / "e.txt").encode())
-    host.dcs_host_free(h)
+    host.dcs_host_graph_free(h)
     # default ostream formatting = %g, 6 significant digits (reference g2o_util.h:98-101,184)
     assert open(tmp_path / "n.txt").read() == "0 0.123457 -1e-07 3.14159\n1 1.23457e+08 0 1\n"
     assert open(tmp_path / "e.txt").read() == "0 1 0\n"
@@ -138,7 +138,7 @@ def test_switches_writer_matches_reference(tmp_path):
     hh = host.dcs_host_read_g2o(path.encode())
     host.dcs_host_add_random_C(hh, 20, 1, 1)
     host.dcs_host_write_switches(hh, mine_f.encode(), priors.ctypes.data_as(C.c_void_p), opt.ctypes.data_as(C.c_void_p), n)
-    host.dcs_host_free(hh)
+    host.dcs_host_graph_free(hh)
     assert filecmp.cmp(mine_f, ref_f, shallow=False)
     assert open(mine_f).readline() == "Odometry EDGES AHEAD\n"
 
@@ -209,7 +209,7 @@ def test_synthetic_generator(tmp_path):
     hh = host.dcs_host_synth_manhattan(5000, 13501, 20260101, C.byref(made))
     path = str(tmp_path / "syn.g2o")
     assert host.dcs_host_write_g2o(hh, path.encode()) == 0
-    host.dcs_host_free(hh)
+    host.dcs_host_graph_free(hh)
     r = Graph.from_g2o(path, 1500, seed=12345)
     assert r.counts == g.counts and np.array_equal(r.pose_xyt, g.pose_xyt) and np.array_equal(r.meas_xyt, g.meas_xyt)
     assert np.array_equal(r.edge_a, g.edge_a) and np.array_equal(r.kind, g.kind)
@@ -234,6 +234,22 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert o.function_tolerance == 1e-6 and o.gradient_tolerance == 1e-10 and o.parameter_tolerance == 1e-8
 
 
+def _exported(path):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path]).decode()
+    return {l.split()[2] for l in out.splitlines() if len(l.split()) == 3 and l.split()[1] in "TDB"}
+
+
+def test_the_two_libraries_export_disjoint_symbols():
+    """libdcs_b200.so exports exactly what include/dcs_b200.h declares (no dev probes), libdcs_host.so only its
+    dcs_host_* entry points, and no name is defined by both (a process that links both must not mix
+    cudaFreeHost with delete)."""
+    cuda, host = _exported(D.lib_path()), _exported(D.host_lib_path())
+    assert cuda == set(D.DECLARED_SYMBOLS), cuda ^ set(D.DECLARED_SYMBOLS)
+    assert host and all(x.startswith("dcs_host_") for x in host), host
+    assert not (cuda & host), cuda & host
+    assert not any("debug" in x or "dbg" in x for x in cuda)
+
+
 def test_no_cpu_fallback_without_device():
     """On a box without a GPU the product path must fail loudly, not compute on the CPU."""
     if D.device_count() > 0:
@@ -255,6 +271,13 @@ def test_bad_arguments_are_rejected_before_touching_cuda():
     bad2.edge_a[0] = g.n_poses
     with pytest.raises(D.DcsError) as ei:
         D.Solver(bad2)
+    assert ei.value.code == 1
+    for fixed in (-2, g.n_poses):                       # -1 means "no constant pose"; anything else must be a pose
+        with pytest.raises(D.DcsError) as ei:
+            D.Solver(Graph(g.pose_xyt, g.edge_a, g.edge_b, g.meas_xyt, g.kind, fixed_pose=fixed))
+        assert ei.value.code == 1
+    with pytest.raises(D.DcsError) as ei:                # one NVSwitch node: at most 8 ranks per handle group
+        D.Solver(g, rank=0, world=9, nccl_unique_id=b"\0" * 128)
     assert ei.value.code == 1
 
 

@@ -6,8 +6,9 @@
 // (row=b,col=a) (only for non-constant rows); a hand-written stable LSD radix sort orders them
 // by (row, col); the sorted list is (i) the full-storage block CSR the SpMV walks and (ii) after
 // a flag+scan unique, the upper-triangular block pattern {(i,i)} U {(min,max)} that the parity
-// hook exports.  The CSR is then re-laid per CTA of 128 rows in jagged-diagonal order so that a
-// thread-per-row kernel reads it fully coalesced with no padding.
+// hook exports.  The CSR is then re-laid per window of kWindow (1024) rows in jagged-diagonal order (rows ranked by
+// degree inside the window, a warp task = 32 consecutive ranks) so that a thread-per-row kernel reads it fully
+// coalesced with no padding.
 #pragma once
 #include "dcs_common.cuh"
 
@@ -266,10 +267,11 @@ __global__ void k_halo_pack(const double4* __restrict__ arr, const int32_t* __re
 // region of the peer that asked for it (peer pointers opened with CUDA IPC; the lists have the same order on
 // both sides, so the destination is dst_base[peer] + position in the peer's slice).  Replaces pack + ncclSend
 // /ncclRecv: one kernel, 32-byte coalesced remote stores, no staging buffer.
+constexpr int kMaxWorld = 8;   // ranks of one handle group = GPUs of one NVSwitch node (dcs_create rejects more)
 struct HaloPeers {
-  double4* ptr[8];        // peer array base (nullptr for self / unused)
-  int32_t send_off[9];    // slices of the send list per peer
-  int32_t dst_base[8];    // first halo entry in the peer's array that belongs to this rank
+  double4* ptr[kMaxWorld];           // peer array base (nullptr for self / unused)
+  int32_t send_off[kMaxWorld + 1];   // slices of the send list per peer
+  int32_t dst_base[kMaxWorld];       // first halo entry in the peer's array that belongs to this rank
   int32_t world;
 };
 constexpr int kPushPerThread = 4;
@@ -288,7 +290,7 @@ k_halo_push(const double4* __restrict__ arr, const int32_t* __restrict__ idx, in
     if (j >= n) continue;
     int r = 0;
 #pragma unroll
-    for (int q = 1; q < 8; ++q) r += (q < P.world && j >= P.send_off[q]) ? 1 : 0;
+    for (int q = 1; q < kMaxWorld; ++q) r += (q < P.world && j >= P.send_off[q]) ? 1 : 0;
     P.ptr[r][P.dst_base[r] + (j - P.send_off[r])] = v[u];
   }
 }

@@ -134,8 +134,8 @@ def load_host_library():
     lib.dcs_host_write_switches.argtypes = [vp, C.c_char_p, vp, vp, C.c_int32]
     lib.dcs_host_write_switches.restype = None
     lib.dcs_host_write_g2o.argtypes = [vp, C.c_char_p]
-    lib.dcs_host_free.argtypes = [vp]
-    lib.dcs_host_free.restype = None
+    lib.dcs_host_graph_free.argtypes = [vp]
+    lib.dcs_host_graph_free.restype = None
     _host = lib
     return lib
 
@@ -233,7 +233,7 @@ class Graph:
                 host.dcs_host_add_random_C(h, n_bogus, seed, 1)
             return cls._from_host(host, h)
         finally:
-            host.dcs_host_free(h)
+            host.dcs_host_graph_free(h)
 
     @classmethod
     def from_g2o_text(cls, text, n_bogus=0, seed=1):
@@ -245,7 +245,7 @@ class Graph:
                 host.dcs_host_add_random_C(h, n_bogus, seed, 1)
             return cls._from_host(host, h)
         finally:
-            host.dcs_host_free(h)
+            host.dcs_host_graph_free(h)
 
     @classmethod
     def synthetic(cls, n_poses, n_loops, n_bogus=0, gen_seed=20260101, bogus_seed=12345):
@@ -262,7 +262,7 @@ class Graph:
             g.loops_made = made.value
             return g
         finally:
-            host.dcs_host_free(h)
+            host.dcs_host_graph_free(h)
 
     def save_npz(self, path, **extra):
         np.savez_compressed(path, pose_xyt=self.pose_xyt, edge_a=self.edge_a, edge_b=self.edge_b,
