@@ -109,6 +109,8 @@ typedef struct dcs_options {
   int32_t rank;
   int32_t world;
   const void* nccl_unique_id;     /* 128-byte ncclUniqueId shared by all ranks           */
+  double max_solver_time_s;       /* 1e6: Solver::Options::max_solver_time_in_seconds (checked between iterations; with
+                                   * world > 1 rank 0's clock decides for everybody)      */
 } dcs_options;
 
 typedef struct dcs_iteration {
@@ -126,6 +128,9 @@ typedef struct dcs_iteration {
   double linear_solver_residual;  /* final PCG |r|/|rhs|                                 */
   double iteration_time_s;
   double cumulative_time_s;
+  double linear_solver_true_residual; /* |(H + Lambda) w - g| / |g| recomputed in fp64 from the returned step w
+                                       * (independent of the PCG recurrence); what replaces "the factorisation is
+                                       * exact" at sizes no direct solver reaches                                */
 } dcs_iteration;
 
 typedef struct dcs_summary {
@@ -176,8 +181,12 @@ DCS_API int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost,
  * D2H cost and gradient (either may be NULL).  The assembled H stays on the device. */
 DCS_API int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* gradient);
 
-/* Same launches with everything resident on the device (used by bench.py's `value`). */
-DCS_API int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total);
+/* Same launches with everything resident on the device (used by bench.py's `value`): `repeats` times the fused
+ * eval + assembly launch (+ its scalar fold), device time in ms.  The assembled product is the reference's structure
+ * (one block per edge + diagonal blocks + gradient).  with_solver_setup != 0 also times the expansion of the edge
+ * blocks into the row storage the PCG's SpMV walks (both triangles; the linear solver's setup, paid once per LM
+ * iteration). */
+DCS_API int dcs_linearize_resident(dcs_handle* h, int32_t repeats, int32_t with_solver_setup, float* ms_total);
 
 /* Cost-only evaluation (candidate point inside LM). */
 DCS_API int dcs_cost(dcs_handle* h, const double* pose_xyt, double* cost);

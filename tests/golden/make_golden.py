@@ -77,6 +77,30 @@ def method2():
     np.savez_compressed(f"{OUT}/method2_traces.npz", **out)
 
 
+def syn10k():
+    """BASELINE config 2 stand-in (M10000.g2o is absent from the reference checkout): 10 000 poses, 20 687 edges + 1000
+    outlier loops, the full 50-iteration DCS solve of the oracle (exact sparse Cholesky: 6 M factor non-zeros because of
+    the random outlier loops, ~7 min on one core - the largest size of this generator family the oracle factors in
+    a reasonable time; 20 K poses with 10 % outliers already needs hours).  -> SYN10K_1000.npz
+    With the default injection seed (12345) the oracle's trajectory runs into the singularity of the reference's own
+    formulation at iteration 38: an edge reaches |cos delta| < 1e-8, the Jet derivative of asin(sin delta) is
+    cos/sqrt(1 - sin^2) = x/0 = inf, the gradient becomes inf and every later step is invalid (FAILURE
+    after 5).  That fixture is kept as the edge case it is (the CUDA path uses sign(cos delta) and stays finite; its
+    trace must match up to that point); `syn10k 777` is the clean 50-iteration trace."""
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345      # outlier-injection seed (srand)
+    tag = "" if seed == 12345 else f"_s{seed}"
+    g = Graph.synthetic(10000, 10688, n_bogus=1000, bogus_seed=seed)
+    ora = O.Oracle(g, dcs_on=True, num_threads=os.cpu_count() or 1)
+    x, s, tr = ora.solve()
+    extra = {f"trace_{k}_dcs1": v for k, v in trace_arrays(tr).items()}
+    fin = ora.evaluate(x)
+    extra.update(final_cost_dcs1=s.final_cost, final_pose_dcs1=x, termination_dcs1=s.termination_type, final_psi_dcs1=fin["psi"],
+                 factor_nnz=s.factor_nnz, oracle_seconds=s.total_time_s)
+    print("SYN10K +1000 dcs 1", s.initial_cost, "->", s.final_cost, "iters", s.num_iterations, "ok", s.num_successful_steps,
+          s.message.decode(), "factor nnz", s.factor_nnz, "%.0f s" % s.total_time_s)
+    g.save_npz(f"{OUT}/SYN10K_1000{tag}.npz", **extra)
+
+
 def structure():
     out = {}
     for name in ("CSAIL", "FR079", "FRH", "INTEL", "M3500", "MIT"):
@@ -100,9 +124,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "method2":     # only the METHOD 2 traces (no reference checkout needed)
         method2()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "syn10k":      # only the synthetic city10000 stand-in (oracle only)
+        syn10k()
+        sys.exit(0)
     assert O.ref_lib() is not None, "build oracle/_ref first (make -C oracle ref)"
     structure()
     solve_case("INTEL", 50)
     solve_case("INTEL", 0)
     solve_case("M3500", 100)
     method2()
+    syn10k()

@@ -95,13 +95,12 @@ __global__ void k_edge_prep(const double* __restrict__ meas, const uint8_t* __re
   dcs_flag[e] = (dcs_on && kind[e] != DCS_EDGE_ODOMETRY) ? 1 : 0;
 }
 
-// sorted half-edge i -> JDS slot: other word + measurement constants
+// sorted half-edge i -> SELL slot: column word (for the SpMV) and the 32-byte record k_linearize streams
 __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const int32_t* __restrict__ slot,
-                                 int32_t nh, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
-                                 const int32_t* __restrict__ deg_all, int32_t fixed, const double* __restrict__ tmx,
+                                 int32_t nh, const int32_t* __restrict__ ea, int32_t fixed, const double* __restrict__ tmx,
                                  const double* __restrict__ tmy, const double* __restrict__ thm,
                                  const uint8_t* __restrict__ dcs_flag, int32_t row_lo, int32_t row_hi, const int32_t* __restrict__ g2l,
-                                 uint32_t* h_other, double* h_tmx, double* h_tmy, double* h_thm, int32_t* edge_slot) {
+                                 uint32_t* cols, HalfEdgeRec* recs, int32_t* edge_slot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const uint32_t v = vals[i];
@@ -120,19 +119,20 @@ __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32
   const bool a_has_row = (a != fixed);
   if ((!side_b && a_has_row) || (side_b && !a_has_row)) word |= kFlagCost;
   const int32_t s = slot[i];
-  h_other[s] = word;
-  h_tmx[s] = tmx[e]; h_tmy[s] = tmy[e]; h_thm[s] = thm[e];
+  cols[s] = word;
+  HalfEdgeRec r;
+  r.tmx = tmx[e]; r.tmy = tmy[e]; r.thm = thm[e]; r.word = word; r.word_next = 0u;   // word_next: k_task_walk
+  recs[s] = r;
   edge_slot[2 * (int64_t)e + (side_b ? 1 : 0)] = s;
-  (void)deg_all; (void)eb;
 }
 
 // mirror_src[slot]: slot of the partner half-edge whose (owner) block this slot mirrors, or -1
 __global__ void k_mirror_src(const uint32_t* __restrict__ vals, const int32_t* __restrict__ slot, int32_t nh,
-                             const uint32_t* __restrict__ h_other, const int32_t* __restrict__ edge_slot, int32_t* mirror_src) {
+                             const uint32_t* __restrict__ cols, const int32_t* __restrict__ edge_slot, int32_t* mirror_src) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const int32_t s = slot[i];
-  const uint32_t word = h_other[s];
+  const uint32_t word = cols[s];
   int32_t src = -1;
   if (!(word & kFlagOwner) && !(word & kFlagOtherFixed)) {
     const uint32_t v = vals[i];
@@ -154,18 +154,25 @@ __global__ void k_is_free(const int32_t* __restrict__ deg_all, int32_t row_lo, i
   is_free[row_pos(rank_of, r)] = (deg_all[row_lo + r] > 0 && (row_lo + r) != fixed) ? 1 : 0;
 }
 
-// parity hook: canonical upper pattern values. One thread per flagged (first-of-run) sorted half-edge.
-__global__ void k_export_upper(const uint64_t* __restrict__ keys, const int32_t* __restrict__ flag_scan, const int32_t* __restrict__ flag,
-                               const int32_t* __restrict__ slot, int32_t nh, const double* __restrict__ Hoff, int64_t ldh,
-                               double* out /* n_upper x 9 */) {
+// parity hook: canonical upper pattern values (block (row, col), row < col).  One thread per flagged (first-of-run)
+// sorted half-edge; duplicate edges between the same pair add up.  The compact array holds every edge's block in
+// the edge's own orientation H_ab, so a half-edge whose row is the b endpoint (an a > b edge) contributes the transpose.
+__global__ void k_export_upper(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const int32_t* __restrict__ flag_scan,
+                               const int32_t* __restrict__ flag, const int32_t* __restrict__ slot, int32_t nh,
+                               const int32_t* __restrict__ block_src, const double* __restrict__ Hup, double* out /* n_upper x 9 */) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh || !flag[i]) return;
   const uint64_t k = keys[i];
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int32_t j = i; j < nh && keys[j] == k; ++j) {   // duplicate edges between the same pair add up
-    const int64_t s = slot[j];
+  for (int32_t j = i; j < nh && keys[j] == k; ++j) {
+    const int32_t src = block_src[slot[j]];
+    if (src < 0) continue;
+    const double* in = Hup + block_base(src);
+    const bool side_b = (vals[j] & 1u) != 0;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) acc[c] += Hoff[(int64_t)c * ldh + s];
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[3 * r + c] += side_b ? in[(3 * c + r) * 32] : in[(3 * r + c) * 32];
   }
   double* o = out + 9 * (int64_t)flag_scan[i];
 #pragma unroll
@@ -189,7 +196,8 @@ struct dcs_handle {
   int32_t rows_per_rank = 0, row_lo = 0, nrows = 0, Npad = 0;
   int32_t e_lo = 0, e_hi = 0;
   int32_t nblk = 0, nh = 0, nwin = 0, ntasks = 0;
-  int64_t ldn = 0, ldh = 0;
+  int64_t ldn = 0, ldh = 0;     // ldh: SELL slots = 32 * (n_slot_tiles + kTailTiles)
+  int64_t n_slot_tiles = 0;
   // graph (device)
   DevBuf<int32_t> ea, eb, deg_all;
   DevBuf<double> e_tmx, e_tmy, e_thm;
@@ -197,17 +205,21 @@ struct dcs_handle {
   // pattern
   DevBuf<uint64_t> keys;        // sorted (row<<32|col)
   DevBuf<uint32_t> vals;        // edge<<1|side
-  DevBuf<int32_t> row_ptr, rp_off, round_ptr, round32, slot, up_flag, up_scan, expand_src, task_obase;
+  DevBuf<int32_t> scan_ws;      // block totals of the K0 scans (all recursion levels)
+  DevBuf<int32_t> row_ptr, slot, up_flag, up_scan, block_src, task_tile0, task_obase;
   DevBuf<uint32_t> rank_info;
-  DevBuf<uint2> first_words;
+  DevBuf<uint4> rowinfo;        // per stored row: degree + the words of rounds 0 and 1
+  DevBuf<int2> task_info;       // per task: first tile, first compact owner-block index
   int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
-  DevBuf<double> Hup;          // [9][ldu] upper-triangular off-diagonal blocks in (task, round, lane) order
+  DevBuf<double> Hup;          // compact edge blocks H_ab, tile-interleaved [ldu / 32][9][32], (task, round, lane) order
   bool mirrored = false;       // Hoff (slot order, both triangles) has been filled from Hup for the current linearization
+  bool mirrored32 = false;     // ... and its single-precision shadow
   DevBuf<uint16_t> rank_of, perm;
   int32_t n_upper = 0;
-  // half-edges (JDS order)
-  DevBuf<uint32_t> h_other;
-  DevBuf<double> h_tmx, h_tmy, h_thm;
+  // half-edges (SELL slot order)
+  DevBuf<uint32_t> cols;        // other pose | flags: what the SpMV streams
+  DevBuf<HalfEdgeRec> recs;     // 32-byte records: what k_linearize / k_cost_rows stream
+  DevBuf<float> Hoff32;         // single-precision shadow of Hoff (mixed-precision PCG only)
   // state
   DevBuf<double4> xyt, cand_xyt, p4;
   DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
@@ -245,16 +257,9 @@ struct dcs_handle {
 
   RowLayout layout() const {
     RowLayout L;
-    L.row_lo = 0; L.nrows = nrows; L.ldn = ldn; L.ldh = ldh;   // gathered arrays are indexed locally: own rows start at 0
-    L.row_ptr = row_ptr.p; L.perm = perm.p; L.rp_off = rp_off.p; L.round_ptr = round_ptr.p;
-    L.nwin = nwin; L.ntasks = ntasks;
-    L.task_obase = task_obase.p; L.ldu = ldu; L.rank_info = rank_info.p; L.round32 = round32.p; L.first_words = first_words.p;
+    L.nrows = nrows; L.ntasks = ntasks; L.ldn = ldn; L.ldh = ldh; L.ldu = ldu;
+    L.rowinfo = rowinfo.p; L.task_info = task_info.p;
     return L;
-  }
-  HalfEdges halfedges() const {
-    HalfEdges H;
-    H.other = h_other.p; H.tmx = h_tmx.p; H.tmy = h_tmy.p; H.thm = h_thm.p;
-    return H;
   }
   EdgeList edgelist() const {
     EdgeList L;
@@ -266,22 +271,29 @@ struct dcs_handle {
 
 namespace {
 
-int scan_exclusive(int32_t* d, int64_t n, cudaStream_t st) {
+// Exclusive scan in place.  `ws` is the handle's scan workspace (block totals of every recursion level, sized once in
+// dcs_create for the largest scan of the pattern build): no allocation and no host synchronisation per call, so the
+// whole K0 build is stream-ordered between the few places that need a count on the host.
+size_t scan_ws_size(int64_t n) {
+  size_t t = 0;
+  while (n > 1) { n = (n + kScanTile - 1) / kScanTile; t += (size_t)n; }
+  return t + 8;
+}
+int scan_exclusive(int32_t* d, int64_t n, cudaStream_t st, int32_t* ws, size_t ws_cap) {
   if (n <= 0) return DCS_OK;
   const int nb = cdiv(n, kScanTile);
-  DevBuf<int32_t> totals;
-  CK(totals.alloc((size_t)nb));
-  LAUNCH(k_scan_tile, nb, kScanThreads, st, d, n, totals.p);
+  if ((size_t)nb > ws_cap) { g_err = "scan_exclusive: workspace too small"; return DCS_ERR_ARG; }
+  LAUNCH(k_scan_tile, nb, kScanThreads, st, d, n, ws);
   if (nb > 1) {
-    CKS(scan_exclusive(totals.p, nb, st));
-    LAUNCH(k_scan_add, nb, kScanThreads, st, d, n, totals.p);
+    CKS(scan_exclusive(ws, nb, st, ws + nb, ws_cap - (size_t)nb));
+    LAUNCH(k_scan_add, nb, kScanThreads, st, d, n, ws);
   }
-  CK(cudaStreamSynchronize(st));   // totals freed on return
   return DCS_OK;
 }
 
 // stable LSD radix sort of (key,val) on the bit range [0,bits_lo) and [32,32+bits_hi)
-int radix_sort(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, int64_t n, int bits_lo, int bits_hi, cudaStream_t st) {
+int radix_sort(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, int64_t n, int bits_lo, int bits_hi, cudaStream_t st,
+               int32_t* ws, size_t ws_cap) {
   if (n <= 1) return DCS_OK;
   DevBuf<uint64_t> k2;
   DevBuf<uint32_t> v2;
@@ -297,12 +309,12 @@ int radix_sort(DevBuf<uint64_t>& keys, DevBuf<uint32_t>& vals, int64_t n, int bi
   for (int s = 0; s < bits_hi; s += 8) shifts.push_back(32 + s);
   for (int shift : shifts) {
     LAUNCH(k_radix_hist, nblk, kSortThreads, st, ki, n, shift, hist.p, nblk);
-    CKS(scan_exclusive(hist.p, (int64_t)256 * nblk, st));
+    CKS(scan_exclusive(hist.p, (int64_t)256 * nblk, st, ws, ws_cap));
     LAUNCH(k_radix_scatter, nblk, kSortThreads, st, ki, vi, ko, vo, n, shift, hist.p, nblk);
     std::swap(ki, ko);
     std::swap(vi, vo);
   }
-  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(st));   // the scratch pair is freed on return
   if (ki != keys.p) {   // odd number of passes: result lives in the scratch pair
     std::swap(keys.p, k2.p);
     std::swap(vals.p, v2.p);
@@ -416,7 +428,7 @@ int build_halo(dcs_handle* h, int32_t nh) {
   CK(scan.alloc((size_t)NP + 1));
   if (nh > 0) LAUNCH(k_halo_mark, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_lo + h->rows_per_rank, need.p);
   CK(cudaMemcpyAsync(scan.p, need.p, ((size_t)NP + 1) * 4, cudaMemcpyDeviceToDevice, st));
-  CKS(scan_exclusive(scan.p, (int64_t)NP + 1, st));
+  CKS(scan_exclusive(scan.p, (int64_t)NP + 1, st, h->scan_ws.p, h->scan_ws.n));
   // receive offsets per owner rank = scan at the rank boundaries
   std::vector<int32_t> bnd(W + 1);
   for (int r = 0; r <= W; ++r) CK(cudaMemcpyAsync(&bnd[r], scan.p + (size_t)r * h->rows_per_rank, 4, cudaMemcpyDeviceToHost, st));
@@ -514,7 +526,7 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 
 // K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
 int linearize(dcs_handle* h, const double4* xyt) {
-  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->Hup.p, h->Hdiag.p,
+  LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->P, h->n_loc, h->Hup.p, h->Hdiag.p,
          h->grad.p, h->task_part.p);
   k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
@@ -524,19 +536,30 @@ int linearize(dcs_handle* h, const double4* xyt) {
   }
   h->have_lin = true;
   h->mirrored = false;
+  h->mirrored32 = false;
   return DCS_OK;
 }
 
-// linear-solver setup: fill the slot-order block storage (both triangles) the row-wise SpMV reads from the compact upper blocks
-int ensure_mirror(dcs_handle* h) {
-  if (h->mirrored || h->nh == 0) { h->mirrored = true; return DCS_OK; }
-  LAUNCH(k_expand, cdiv(h->nh, 256), 256, h->stream, h->expand_src.p, h->nh, h->ldh, h->ldu, h->Hup.p, h->Hoff.p);
-  h->mirrored = true;
+// linear-solver setup: fill the slot-order block storage (both triangles) the row-wise SpMV reads from the compact
+// edge blocks; `single`: the single-precision shadow used by the mixed-precision inner iterations
+int ensure_mirror(dcs_handle* h, bool single = false) {
+  if (single) {
+    if (!h->mirrored32) {
+      if (!h->Hoff32.p) CK(h->Hoff32.alloc_zero(9 * (size_t)h->ldh, h->stream));
+      LAUNCH(k_expand<float>, cdiv(h->ldh, 256), 256, h->stream, h->block_src.p, h->cols.p, h->ldh, h->Hup.p, h->Hoff32.p);
+      h->mirrored32 = true;
+    }
+    return DCS_OK;
+  }
+  if (!h->mirrored) {
+    LAUNCH(k_expand<double>, cdiv(h->ldh, 256), 256, h->stream, h->block_src.p, h->cols.p, h->ldh, h->Hup.p, h->Hoff.p);
+    h->mirrored = true;
+  }
   return DCS_OK;
 }
 
 int cost_only(dcs_handle* h, const double4* xyt, int slot) {
-  LAUNCH(k_cost_rows, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->halfedges(), h->P, h->task_part.p);
+  LAUNCH(k_cost_rows, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->P, h->n_loc, h->task_part.p);
   k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + slot, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + slot, 1));
@@ -545,7 +568,7 @@ int cost_only(dcs_handle* h, const double4* xyt, int slot) {
 
 // one PCG iteration on the stream (capturable)
 int pcg_iteration(dcs_handle* h, const double* D) {
-  LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->task_part.p);
+  LAUNCH(k_spmv<double>, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
   k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
   CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
@@ -572,7 +595,7 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
   LAUNCH(k_precond, h->vec_grid(), 256, h->stream, h->Hdiag.p, h->lmdiag.p, h->scale.p, h->is_free.p, h->nrows, h->ldn, inv_radius,
          lambda_explicit, h->Adiag.p, h->Minv.p);
   if (h->opt.preconditioner == 1) {
-    LAUNCH(k_chain_factor, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->rank_of.p, h->nrows, h->ldn,
+    LAUNCH(k_chain_factor<double>, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->rank_of.p, h->nrows, h->ldn,
            h->ldh, h->chL.p, h->chS.p);
     LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->perm.p, 0, h->nrows,
            h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
@@ -658,6 +681,7 @@ void dcs_options_default(dcs_options* o) {
   o->rank = 0;
   o->world = 1;
   o->nccl_unique_id = nullptr;
+  o->max_solver_time_s = 1e6;
 }
 
 void* dcs_host_alloc(uint64_t bytes) {
@@ -799,6 +823,10 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
 
   lap("upload + edge prep");
   // ---- K0: half-edges, sort, CSR, jagged-diagonal re-layout ---------------------------------------
+  {
+    const int64_t max_scan = std::max<int64_t>({2 * (int64_t)E + 2, (int64_t)h->Npad + 2, 256 * ((int64_t)cdiv(2 * (int64_t)E + 1, kSortTile) + 1)});
+    CK(h->scan_ws.alloc(scan_ws_size(max_scan)));
+  }
   CK(h->deg_all.alloc_zero((size_t)h->Npad, st));
   if (E > 0) LAUNCH(k_pose_degree, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->deg_all.p);
   CK(h->is_free.alloc_zero((size_t)h->ldn, st));
@@ -807,7 +835,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(he_off.alloc_zero((size_t)E + 1, st));
   const int32_t row_hi = h->row_lo + h->nrows;
   if (E > 0) LAUNCH(k_halfedge_count, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->fixed, h->row_lo, row_hi, he_off.p);
-  CKS(scan_exclusive(he_off.p, (int64_t)E + 1, st));
+  CKS(scan_exclusive(he_off.p, (int64_t)E + 1, st, h->scan_ws.p, h->scan_ws.n));
   int32_t nh = 0;
   CK(cudaMemcpyAsync(&nh, he_off.p + E, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -817,7 +845,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->vals.alloc((size_t)std::max(nh, 1)));
   if (E > 0) LAUNCH(k_halfedge_fill, cdiv(E, 256), 256, st, h->ea.p, h->eb.p, E, h->fixed, h->row_lo, row_hi, he_off.p, h->keys.p, h->vals.p);
   const int nb = bits_for(std::max(N, 2));
-  CKS(radix_sort(h->keys, h->vals, nh, 28, nb, st));   // column word: 27 index bits + the owner-order bit
+  CKS(radix_sort(h->keys, h->vals, nh, 28, nb, st, h->scan_ws.p, h->scan_ws.n));   // column word: 27 index bits + the owner-order bit
 
   lap("half-edges + radix sort");
   CK(h->row_ptr.alloc((size_t)h->ldn + 1));
@@ -827,57 +855,63 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     LAUNCH(k_row_ptr, cdiv(rows + 1, 256), 256, st, h->keys.p, nh, h->row_lo, rows, h->row_ptr.p);
   }
   CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
-  CK(h->rp_off.alloc_zero((size_t)h->nwin + 1, st));
-  CK(h->rank_info.alloc((size_t)h->ldn)); CK(h->round32.alloc((size_t)h->nwin * 32));
-  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rank_info.p, h->rp_off.p);
-  if (h->nrows > 0)   // per-row arrays live in (window, rank) order from here on
-    if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->rank_of.p, h->is_free.p);
-  CKS(scan_exclusive(h->rp_off.p, (int64_t)h->nwin + 1, st));
-  int32_t n_rounds = 0;
-  CK(cudaMemcpyAsync(&n_rounds, h->rp_off.p + h->nwin, 4, cudaMemcpyDeviceToHost, st));
+  CK(h->rank_info.alloc((size_t)h->ldn));
+  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rank_info.p);
+  // per-row arrays live in (window, rank) order from here on
+  if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->rank_of.p, h->is_free.p);
+  // SELL tiles: a task's tile count = its largest degree (first lane: ranks are degree-sorted); tile0 = exclusive scan
+  CK(h->task_tile0.alloc_zero((size_t)h->ntasks + 1, st));
+  LAUNCH(k_task_kmax, cdiv(h->ntasks, 256), 256, st, h->ntasks, h->rank_info.p, h->task_tile0.p);
+  CKS(scan_exclusive(h->task_tile0.p, (int64_t)h->ntasks + 1, st, h->scan_ws.p, h->scan_ws.n));
+  int32_t n_tiles = 0;
+  CK(cudaMemcpyAsync(&n_tiles, h->task_tile0.p + h->ntasks, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  CK(h->round_ptr.alloc((size_t)std::max(n_rounds, 1)));
-  LAUNCH(k_jds_rounds, h->nwin, kWindow, st, h->row_ptr.p, (int32_t)h->ldn, h->rp_off.p, h->round_ptr.p, h->round32.p);
+  if ((int64_t)n_tiles + kTailTiles >= (int64_t)1 << 26) { g_err = "dcs_create: more than 2^31 half-edge slots on one rank"; return DCS_ERR_ARG; }
+  h->n_slot_tiles = n_tiles;
+  h->ldh = ((int64_t)n_tiles + kTailTiles) * kSlice;
   CK(h->slot.alloc((size_t)std::max(nh, 1)));
-  if (nh > 0) LAUNCH(k_jds_slot, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_ptr.p, h->rank_of.p, h->rp_off.p,
-                     h->round_ptr.p, h->slot.p);
+  if (nh > 0) LAUNCH(k_sell_slot, cdiv(nh, 256), 256, st, h->keys.p, nh, h->row_lo, h->row_ptr.p, h->rank_of.p, h->task_tile0.p, h->slot.p);
 
   CKS(build_halo(h, nh));      // halo lists + the global -> local index map the half-edge words use
   const size_t HH = (size_t)h->ldh;
-  CK(h->h_other.alloc_zero(HH, st)); CK(h->h_tmx.alloc_zero(HH, st)); CK(h->h_tmy.alloc_zero(HH, st)); CK(h->h_thm.alloc_zero(HH, st));
-  CK(h->expand_src.alloc((size_t)std::max(nh, 1)));
-  CK(h->first_words.alloc_zero((size_t)h->ldn, st));
+  CK(h->cols.alloc_zero(HH, st)); CK(h->recs.alloc_zero(HH, st));          // padding slots: word 0, zero record
+  CK(h->block_src.alloc(HH));
+  CK(cudaMemsetAsync(h->block_src.p, 0xFF, HH * 4, st));                    // -1: no block
+  CK(h->rowinfo.alloc_zero((size_t)h->ldn, st));
   CK(h->task_obase.alloc_zero((size_t)h->ntasks + 1, st));
-  if (nh > 0) {
-    DevBuf<int32_t> mirror_src, cidx;
-    CK(mirror_src.alloc((size_t)nh)); CK(cidx.alloc((size_t)nh));
-    DevBuf<int32_t> edge_slot;
+  CK(h->task_info.alloc((size_t)h->ntasks + 1));
+  {
+    DevBuf<int32_t> mirror_src, cidx, edge_slot;
+    CK(mirror_src.alloc(HH)); CK(cidx.alloc(HH));
     CK(edge_slot.alloc((size_t)2 * EE));
     CK(cudaMemsetAsync(edge_slot.p, 0xFF, (size_t)2 * EE * 4, st));
-    LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->eb.p, h->deg_all.p,
-           h->fixed, h->e_tmx.p, h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->g2l.p, h->h_other.p,
-           h->h_tmx.p, h->h_tmy.p, h->h_thm.p, edge_slot.p);
-    LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->h_other.p, edge_slot.p, mirror_src.p);
-    LAUNCH(k_first_words, cdiv(h->ldn, 256), 256, st, h->layout(), h->h_other.p, h->first_words.p);
+    CK(cudaMemsetAsync(mirror_src.p, 0xFF, HH * 4, st));
+    if (nh > 0) {
+      LAUNCH(k_fill_halfedges, cdiv(nh, 256), 256, st, h->keys.p, h->vals.p, h->slot.p, nh, h->ea.p, h->fixed, h->e_tmx.p,
+             h->e_tmy.p, h->e_thm.p, h->e_dcs.p, h->row_lo, row_hi, h->g2l.p, h->cols.p, h->recs.p, edge_slot.p);
+      LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->cols.p, edge_slot.p, mirror_src.p);
+    }
     // compact owner-block order = the order k_linearize meets the owner half-edges in
-    LAUNCH(k_owner_enum<false>, h->ntasks, kRowsPerBlock, st, h->layout(), h->h_other.p, h->task_obase.p, (int32_t*)nullptr);
-    CKS(scan_exclusive(h->task_obase.p, (int64_t)h->ntasks + 1, st));
+    LAUNCH(k_task_walk<false>, h->ntasks, kRowsPerBlock, st, h->ntasks, h->rank_info.p, h->task_tile0.p, (const int32_t*)nullptr,
+           h->cols.p, h->task_obase.p, (int32_t*)nullptr, (HalfEdgeRec*)nullptr, (uint4*)nullptr);
+    CKS(scan_exclusive(h->task_obase.p, (int64_t)h->ntasks + 1, st, h->scan_ws.p, h->scan_ws.n));
     int32_t n_own = 0;
     CK(cudaMemcpyAsync(&n_own, h->task_obase.p + h->ntasks, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    LAUNCH(k_task_walk<true>, h->ntasks, kRowsPerBlock, st, h->ntasks, h->rank_info.p, h->task_tile0.p, h->task_obase.p, h->cols.p,
+           (int32_t*)nullptr, cidx.p, h->recs.p, h->rowinfo.p);
+    LAUNCH(k_task_info, cdiv(h->ntasks + 1, 256), 256, st, h->ntasks, h->task_tile0.p, h->task_obase.p, h->task_info.p);
+    if (nh > 0) LAUNCH(k_block_src, cdiv(nh, 256), 256, st, h->cols.p, h->slot.p, mirror_src.p, cidx.p, nh, h->block_src.p);
+    CK(cudaStreamSynchronize(st));     // n_own on the host; the scratch arrays are freed here
     h->ldu = ((int64_t)std::max(n_own, 1) + 31) / 32 * 32;
-    LAUNCH(k_owner_enum<true>, h->ntasks, kRowsPerBlock, st, h->layout(), h->h_other.p, (int32_t*)nullptr, cidx.p);
-    LAUNCH(k_expand_src, cdiv(nh, 256), 256, st, h->h_other.p, mirror_src.p, cidx.p, nh, h->expand_src.p);
-    CK(cudaStreamSynchronize(st));
   }
 
-  lap("jds layout + fill");
+  lap("sell layout + fill");
   // unique upper pattern (parity hook)
   CK(h->up_flag.alloc_zero((size_t)nh + 1, st)); CK(h->up_scan.alloc_zero((size_t)nh + 1, st));
   if (nh > 0) {
     LAUNCH(k_upper_flag, cdiv(nh, 256), 256, st, h->keys.p, nh, h->fixed, h->up_flag.p);
     CK(cudaMemcpyAsync(h->up_scan.p, h->up_flag.p, (size_t)(nh + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    CKS(scan_exclusive(h->up_scan.p, (int64_t)nh + 1, st));
+    CKS(scan_exclusive(h->up_scan.p, (int64_t)nh + 1, st, h->scan_ws.p, h->scan_ws.n));
     CK(cudaMemcpyAsync(&h->n_upper, h->up_scan.p + nh, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
@@ -973,11 +1007,14 @@ int dcs_linearize(dcs_handle* h, const double* pose_xyt, double* cost, double* g
   return DCS_OK;
 }
 
-int dcs_linearize_resident(dcs_handle* h, int32_t repeats, float* ms_total) {
+int dcs_linearize_resident(dcs_handle* h, int32_t repeats, int32_t with_solver_setup, float* ms_total) {
   if (!h || repeats <= 0) return DCS_ERR_ARG;
   CK(cudaSetDevice(h->dev));
   CK(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < repeats; ++i) CKS(linearize(h, h->xyt.p));
+  for (int i = 0; i < repeats; ++i) {
+    CKS(linearize(h, h->xyt.p));
+    if (with_solver_setup) CKS(ensure_mirror(h));   // + the row-storage expansion the PCG needs (once per LM iteration)
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
   float ms = 0;
@@ -1058,8 +1095,8 @@ int dcs_get_hessian(dcs_handle* h, double* block_values) {
   if (nh > 0) {
     DevBuf<double> d_up;
     CK(d_up.alloc_zero(up.size(), h->stream));
-    CKS(ensure_mirror(h));     // slot-order copy of the compact upper blocks
-    LAUNCH(k_export_upper, cdiv(nh, 256), 256, h->stream, h->keys.p, h->up_scan.p, h->up_flag.p, h->slot.p, nh, h->Hoff.p, h->ldh, d_up.p);
+    LAUNCH(k_export_upper, cdiv(nh, 256), 256, h->stream, h->keys.p, h->vals.p, h->up_scan.p, h->up_flag.p, h->slot.p, nh, h->block_src.p,
+           h->Hup.p, d_up.p);
     CK(cudaMemcpyAsync(up.data(), d_up.p, up.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(keys.data(), h->keys.p, (size_t)nh * 8, cudaMemcpyDeviceToHost));
@@ -1189,6 +1226,18 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
   if (it.gradient_max_norm <= o.gradient_tolerance) { term = DCS_CONVERGENCE; msg = "Gradient tolerance reached."; }
   else
   for (;;) {
+    {   // MaxSolverTimeReached; with several ranks rank 0's clock decides for everybody
+      bool out_of_time = now_s() - t_start >= o.max_solver_time_s;
+      if (h->world > 1 && o.max_solver_time_s < 1e6) {
+        h->h_rank_scal[0] = (h->rank == 0 && out_of_time) ? 1.0 : 0.0;
+        CK(cudaMemcpyAsync(h->rank_scal.p, h->h_rank_scal, sizeof(double), cudaMemcpyHostToDevice, st));
+        CKS(allreduce_sum(h, h->rank_scal.p, 1));
+        CK(cudaMemcpyAsync(h->h_rank_scal, h->rank_scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out_of_time = h->h_rank_scal[0] > 0.5;
+      }
+      if (out_of_time) { term = DCS_NO_CONVERGENCE; msg = "Maximum solver time reached."; break; }
+    }
     if (prev.iteration >= o.max_num_iterations) { term = DCS_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
     if (prev.gradient_max_norm <= o.gradient_tolerance) { term = DCS_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
     if (radius <= o.min_trust_region_radius) { term = DCS_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
@@ -1211,10 +1260,14 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
     CKS(halo_exchange(h, h->p4.p));
     CKS(ensure_mirror(h));
-    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, h->Hdiag.p, h->q.p, h->task_part.p);
+    LAUNCH(k_spmv<double>, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, h->Hdiag.p, h->n_loc, h->q.p, h->task_part.p);
     k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + S_WHW, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches;
     CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
+    // true residual |(H + Lambda) w - g| / |g| of this step's linear solve, from q = H w just formed
+    LAUNCH(k_true_residual, h->vec_grid(), kVecThreads, st, h->grad.p, h->q.p, h->w.p, h->lmdiag.p, h->scale.p, h->is_free.p,
+           h->nrows, h->ldn, 1.0 / radius, h->partials.p, h->tickets.p + 4, h->scal.p);
+    CKS(allreduce_sum(h, h->scal.p + S_TRES, 1));
     // candidate = x - w
     LAUNCH(k_apply_step, h->vec_grid(), kVecThreads, st, h->xyt.p, h->w.p, h->is_free.p, 0, h->nrows, h->ldn, h->cand_xyt.p,
            h->partials.p, h->tickets.p + 5, h->scal.p);
@@ -1227,6 +1280,7 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->eval_ms += ms;
     const double wg = h->h_scal[S_WG], whw = h->h_scal[S_WHW];
+    it.linear_solver_true_residual = h->h_scal[S_RR0] > 0.0 ? std::sqrt(h->h_scal[S_TRES] / h->h_scal[S_RR0]) : 0.0;
     const double model_cost_change = wg - 0.5 * whw;
     const bool finite_step = std::isfinite(wg) && std::isfinite(whw) && std::isfinite(h->h_scal[S_STEP_SQ]);
     it.step_is_valid = finite_step && model_cost_change > 0.0;

@@ -12,9 +12,12 @@ namespace dcs {
 // ------------------------------------------------------------------------------------------
 constexpr int kRowsPerBlock = 32;        // threads per CTA in the row-owner kernels: ONE warp task per CTA, so a
                                          // finished task frees its registers at once (no sibling warp to wait for)
-constexpr int kWindow = 1024;            // rows per jagged-diagonal window (sorted by degree inside it)
-constexpr int kSlice = 32;               // rows per warp task
+constexpr int kWindow = 1024;            // rows per sorting window (rows ranked by degree inside it)
+constexpr int kSlice = 32;               // rows per warp task = lanes of a tile
 constexpr int kSlicesPerWindow = kWindow / kSlice;
+constexpr int kK1Rounds = 2;             // rounds per pipeline stage of k_linearize; a half-edge record carries the index
+                                         // word of the round kK1Rounds later (baked into the data by the pattern build)
+constexpr int kTailTiles = 4;            // zero tiles after the last task (prefetch addresses are clamped, this is slack)
 constexpr uint32_t kKeyNonOwner = 1u << 27;  // sort-key bit just above the 27 column bits: non-owner half-edges follow a
                                              // row's owner ones (the radix sort covers bits 0..27 of the column word)
 constexpr uint32_t kIdxMask = 0x07FFFFFFu;  // low 27 bits of a half-edge word: other pose (<= 134M poses)
@@ -154,19 +157,53 @@ __device__ __forceinline__ double fast_rsqrt(double x) {    // x normal, > 0
   e = fma(-x * y, y, 1.0);
   return fma(h, e, y);
 }
-__device__ __forceinline__ double fold_angle_fast(double d, double* sigma) {
-  const double inv2pi = 0.15915494309189533577;
-  const double twopi_hi = 6.283185307179586232;
-  const double twopi_lo = 2.4492935982947064e-16;
-  const double pi = 3.141592653589793116;
-  const double half_pi = 1.5707963267948966;
-  const double magic = 6755399441055744.0;              // 1.5 * 2^52: round-to-nearest-integer by addition
-  const double k = fma(d, inv2pi, magic) - magic;
-  double t = fma(-k, twopi_hi, d);
-  t = fma(-k, twopi_lo, t);
-  const bool hi = t > half_pi, lo = t < -half_pi;
-  *sigma = (hi || lo) ? -1.0 : 1.0;
-  return hi ? (pi - t) : (lo ? (-pi - t) : t);
+// ---- transcendental-free helpers of the hot path -------------------------------------------------------------------
+// Numeric constants live in __constant__ memory: fp64 instructions take a constant-bank operand directly, whereas an
+// immediate costs two UMOVs per use inside the loop (37 per round in the round-1 kernel).
+struct MathConsts {
+  double magic;            // 1.5 * 2^52: round-to-nearest-integer by addition
+  double inv_pi, pi_hi, pi_lo;
+  double two_over_pi, pio2_hi, pio2_lo;
+  double s1, s2, s3, s4, s5, s6;   // fdlibm __kernel_sin
+  double c1, c2, c3, c4, c5, c6;   // fdlibm __kernel_cos
+};
+__constant__ MathConsts kMath = {
+    6755399441055744.0,
+    0.31830988618379067154, 3.141592653589793116, 1.2246467991473532e-16,
+    0.63661977236758134308, 1.5707963267948966, 6.123233995736766e-17,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
+// t = d - rint(d / pi) * pi  in [-pi/2, pi/2].  The reference's angle row is asin(sin d) = sigma t with
+// sigma = sign(cos d) = (-1)^rint(d/pi) (also its derivative); the normal-equation terms only ever need
+// sigma * e_th = t and e_th^2 = t^2, so neither sigma nor the signed value is formed.
+__device__ __forceinline__ double fold_pi(double d) {
+  const double k = fma(d, kMath.inv_pi, kMath.magic) - kMath.magic;
+  return fma(-k, kMath.pi_lo, fma(-k, kMath.pi_hi, d));
+}
+
+// sin / cos of a pose angle (|x| < ~1e6): two-term Cody-Waite reduction by pi/2 (the products are exact inside the
+// fma, absolute error ~1e-16) and the fdlibm kernel polynomials (< 1 ulp on [-pi/4, pi/4]).  Leaner than the inlined
+// sincos(): no Payne-Hanek slow path, no special-value handling, coefficients as constant-bank operands.
+__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
+  const double kd = fma(x, kMath.two_over_pi, kMath.magic);
+  const int q = __double2loint(kd);
+  const double k = kd - kMath.magic;
+  const double r = fma(-k, kMath.pio2_lo, fma(-k, kMath.pio2_hi, x));
+  const double z = r * r;
+  double ps = fma(z, kMath.s6, kMath.s5);
+  ps = fma(z, ps, kMath.s4); ps = fma(z, ps, kMath.s3); ps = fma(z, ps, kMath.s2); ps = fma(z, ps, kMath.s1);
+  const double s = fma(r * z, ps, r);
+  double pc = fma(z, kMath.c6, kMath.c5);
+  pc = fma(z, pc, kMath.c4); pc = fma(z, pc, kMath.c3); pc = fma(z, pc, kMath.c2); pc = fma(z, pc, kMath.c1);
+  const double c = fma(z, fma(z, pc, -0.5), 1.0);
+  const bool swap = (q & 1) != 0;
+  const double ss = swap ? c : s, cc = swap ? s : c;
+  // quadrant signs by flipping the sign bit: sin negative for q = 2, 3; cos negative for q = 1, 2
+  sn = __hiloint2double(__double2hiint(ss) ^ ((q & 2) << 30), __double2loint(ss));
+  cs = __hiloint2double(__double2hiint(cc) ^ (((q + 1) & 2) << 30), __double2loint(cc));
 }
 
 struct EdgeTerms {
@@ -182,70 +219,76 @@ struct EdgeTerms {
   double cost;
 };
 
-__device__ __forceinline__ double edge_cost_terms(double xa, double ya, double tha,
-                                                  double xb, double yb, double thb,
-                                                  double tmx, double tmy, double thm,
-                                                  bool dcs, const Params& P,
-                                                  double& q00, double& q01, double& dxw, double& dyw, double& epx, double& epy,
-                                                  double& ex, double& ey, double& eth, double& sigma,
-                                                  double& psi2, double& inv_den, double& e2, double& rho1) {
-  sincos(tha + thm, &q01, &q00);            // one sincos per half-edge instead of streaming cos/sin of the
-                                            // measurement and gathering cos/sin of the pose (28 B less traffic)
-  dxw = xb - xa; dyw = yb - ya;
-  epx = fma(q00, dxw, q01 * dyw);
-  epy = fma(q00, dyw, -q01 * dxw);
-  ex = epx - tmx; ey = epy - tmy;
-  eth = fold_angle_fast(thb - tha - thm, &sigma);
-  const double res = fma(ex, ex, ey * ey);
-  e2 = fma(eth, eth, res);
-  psi2 = 1.0; inv_den = 0.0;
-  if (dcs && res > P.phi) {                 // <=> psi_org < 1
-    inv_den = fast_rcp(P.phi + res);
-    psi2 = 2.0 * P.phi * inv_den;
-  }
-  const double s = psi2 * e2;
-  rho1 = 1.0;
-  double cost = 0.5 * s;
-  if (s > P.hub_b) {
-    const double rs = fast_rsqrt(s);
-    rho1 = P.hub_a * rs;                    // >= DBL_MIN for every finite s
-    cost = fma(P.hub_a, s * rs, -0.5 * P.hub_b);
-  }
-  return cost;
+// Row-owner frame of a half-edge.  The row pose o and the other pose p give the edge frame (a = first endpoint,
+// b = second) without selecting six doubles: d = tb - ta = +-(p - o) is a sign-bit flip with the word's side bit
+// (bit 31 = kFlagSideB = the IEEE sign position), only the angle of pose a needs a select.
+struct EdgeFrame { double dxw, dyw, sdth, tha; };
+__device__ __forceinline__ double flip_sign(double v, uint32_t sign_mask) {
+  return __hiloint2double(__double2hiint(v) ^ (int)sign_mask, __double2loint(v));
+}
+__device__ __forceinline__ EdgeFrame edge_frame(double ox, double oy, double oth, double px, double py, double pth, uint32_t word) {
+  const uint32_t sgn = word & kFlagSideB;
+  EdgeFrame F;
+  F.dxw = flip_sign(px - ox, sgn);
+  F.dyw = flip_sign(py - oy, sgn);
+  F.sdth = flip_sign(pth - oth, sgn);         // thb - tha
+  F.tha = sgn ? pth : oth;
+  return F;
 }
 
-__device__ __forceinline__ void edge_terms(double xa, double ya, double tha,
-                                           double xb, double yb, double thb,
-                                           double tmx, double tmy, double thm,
-                                           bool dcs, const Params& P, EdgeTerms& T) {
-  double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
-  T.cost = edge_cost_terms(xa, ya, tha, xb, yb, thb, tmx, tmy, thm, dcs, P, q00, q01, dxw, dyw, epx, epy,
-                           ex, ey, eth, sigma, psi2, inv_den, e2, rho1);
-  const double alpha = rho1 * psi2;
-  const double c2 = -alpha * inv_den;                       // 0 unless DCS active
-  const double c1 = fma(alpha * e2, inv_den * inv_den, 2.0 * c2);
-  const double beta = fma(c2, e2, alpha);
-  const double f0 = fma(q00, ex, -q01 * ey);                // Q^T exy
-  const double f1 = fma(q01, ex, q00 * ey);
-  const double et = fma(ex, epy, -ey * epx);                // exy . t
-  const double tt = fma(epx, epx, epy * epy);               // |t|^2
+// cost of one edge and the intermediates the normal-equation terms reuse
+struct EdgeCore { double q00, q01, epx, epy, ex, ey, t, psi2, inv_den, e2, rho1, cost; };
+__device__ __forceinline__ EdgeCore edge_core(const EdgeFrame& F, double tmx, double tmy, double thm, bool dcs, const Params& P) {
+  EdgeCore C;
+  sincos_cw(F.tha + thm, C.q01, C.q00);     // Q = Rm^T Ra^T = R(-(tha + thm)); one sincos per half-edge instead of
+                                            // streaming cos/sin of the measurement and gathering cos/sin of the pose
+  C.epx = fma(C.q00, F.dxw, C.q01 * F.dyw);
+  C.epy = fma(C.q00, F.dyw, -C.q01 * F.dxw);
+  C.ex = C.epx - tmx; C.ey = C.epy - tmy;
+  C.t = fold_pi(F.sdth - thm);              // sigma * e_th
+  const double res = fma(C.ex, C.ex, C.ey * C.ey);
+  C.e2 = fma(C.t, C.t, res);
+  // DCS (psi_org < 1 <=> res > phi) and Huber, branch-free: nearly every warp has a lane on either side of both
+  // thresholds, so the reciprocal and the reciprocal square root are always computed and selected afterwards
+  const bool active = dcs && res > P.phi;
+  const double inv = fast_rcp(P.phi + res);
+  C.inv_den = active ? inv : 0.0;
+  C.psi2 = active ? 2.0 * P.phi * inv : 1.0;
+  const double s = C.psi2 * C.e2;
+  const bool lin = s > P.hub_b;
+  const double rs = fast_rsqrt(lin ? s : 1.0);
+  C.rho1 = lin ? P.hub_a * rs : 1.0;          // >= DBL_MIN for every finite s
+  C.cost = lin ? fma(P.hub_a, s * rs, -0.5 * P.hub_b) : 0.5 * s;
+  return C;
+}
+
+__device__ __forceinline__ void edge_terms(const EdgeFrame& F, const EdgeCore& C, EdgeTerms& T) {
+  const double alpha = C.rho1 * C.psi2;
+  const double c2 = -alpha * C.inv_den;                       // 0 unless DCS active
+  const double c1 = fma(alpha * C.e2, C.inv_den * C.inv_den, 2.0 * c2);
+  const double beta = fma(c2, C.e2, alpha);
+  const double f0 = fma(C.q00, C.ex, -C.q01 * C.ey);          // Q^T exy
+  const double f1 = fma(C.q01, C.ex, C.q00 * C.ey);
+  const double et = fma(C.ex, C.epy, -C.ey * C.epx);          // exy . t
+  const double tt = fma(C.epx, C.epx, C.epy * C.epy);         // |t|^2
   const double cf0 = c1 * f0, cf1 = c1 * f1;
   T.U00 = fma(cf0, f0, alpha);
   T.U01 = cf0 * f1;
   T.U11 = fma(cf1, f1, alpha);
-  const double k2 = c2 * eth * sigma;                       // sigma c2 eth
+  const double k2 = c2 * C.t;                                 // sigma c2 eth
   T.sc0 = k2 * f0; T.sc1 = k2 * f1;
   const double k1 = c1 * et;
-  T.e0 = fma(k1, f0, fma(alpha, dyw, -T.sc0));              // dv - sigma c, dv = alpha n + k1 f, n = (dyw, -dxw)
-  T.e1 = fma(k1, f1, fma(-alpha, dxw, -T.sc1));
-  const double sts2 = k2 * et;                              // sigma ts2
+  T.e0 = fma(k1, f0, fma(alpha, F.dyw, -T.sc0));              // dv - sigma c, dv = alpha n + k1 f, n = (dyw, -dxw)
+  T.e1 = fma(k1, f1, fma(-alpha, F.dxw, -T.sc1));
+  const double sts2 = k2 * et;                                // sigma ts2
   T.alpha = alpha;
   T.k22 = fma(k1, et, fma(alpha, tt + 1.0, -2.0 * sts2));
   T.o22 = sts2 - alpha;
   T.bf0 = beta * f0; T.bf1 = beta * f1;
-  const double sae = sigma * alpha * eth;
+  const double sae = alpha * C.t;                             // sigma alpha eth
   T.ga = fma(beta, et, -sae);
   T.gb = sae;
+  T.cost = C.cost;
 }
 
 // Own rows are STORED in (window, rank) order - the order the row-owner kernels walk them in - so that every
@@ -280,6 +323,10 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t po
 }
 __device__ __forceinline__ void st_stream(double* p, double v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+// bulk L2 prefetch of a contiguous range (address and size multiples of 16 bytes); asynchronous, no destination
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 // gathered operands (poses, the PCG direction vector): small, reused by every row that references them
 __device__ __forceinline__ double4 ld_keep4(const double4* p, uint64_t pol) {

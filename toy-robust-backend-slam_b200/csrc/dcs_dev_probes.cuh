@@ -5,27 +5,22 @@
 
 namespace {
 
-// development probe: K1's memory traffic as a flat, dependency-free stream (one thread per half-edge slot)
-__global__ void k_dbg_flat(const uint32_t* __restrict__ other, const double* __restrict__ tmx, const double* __restrict__ tmy,
-                           const double* __restrict__ thm, const double4* __restrict__ xyt, int32_t nh, int64_t ldh, double* Hoff,
-                           int mode) {
+// development probe: K1's memory traffic as a flat, dependency-free stream (one thread per half-edge slot):
+// mode bit 0: gather the other pose; bit 1: store a 3x3 block per owner slot into the compact tile-interleaved array
+__global__ void k_dbg_flat(const HalfEdgeRec* __restrict__ recs, const double4* __restrict__ xyt, int64_t nslots, double* Hup, int64_t ldu, int mode) {
   const L2Policy pol = make_l2_policy();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nh) return;
-  const uint32_t w = ld_stream_u32(other + i, pol.stream);
-  double a = ld_stream(tmx + i, pol.stream), b = ld_stream(tmy + i, pol.stream), c = ld_stream(thm + i, pol.stream);
-  if (mode & 1) { const double4 p = ld_keep4(xyt + (w & kIdxMask), pol.keep); a += p.x; b += p.y; c += p.z; }
-  if ((mode & 2) && ((w & kFlagOwner) || (mode & 4))) {
-    if (mode & 8) {         // tile-interleaved: [slot/32][9][32]
-      double* o = Hoff + (i >> 5) * 288 + (i & 31);
+  if (i >= nslots) return;
+  HalfEdgeRec r;
+  ld_rec(r, recs + i, pol.stream);
+  double a = r.tmx, b = r.tmy, c = r.thm;
+  if (mode & 1) { PoseRec p; ld_pose(p, xyt + (r.word & kIdxMask), pol.keep); a += p.x; b += p.y; c += p.th; }
+  if ((mode & 2) && (r.word & kFlagOwner)) {
+    double* o = Hup + block_base((i >> 1) % ldu);       // ~ the compact array's footprint
 #pragma unroll
-      for (int k = 0; k < 9; ++k) st_stream(o + k * 32, a + k * b + c, pol.stream);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) st_stream(Hoff + (int64_t)k * ldh + i, a + k * b + c, pol.stream);
-    }
+    for (int k = 0; k < 9; ++k) st_stream(o + k * 32, a + k * b + c, pol.stream);
   }
-  if (!(mode & 2) && a + b + c == 1.2345e300) Hoff[i] = a;
+  if (!(mode & 2) && a + b + c == 1.2345e300) Hup[i] = a;
 }
 
 // development probe: scatter-add cost of an edge-centric assembly (18 fp64 reductions per edge into the
@@ -47,10 +42,11 @@ extern "C" {
 // development probe (not part of the public header): time the flat traffic kernel; returns us per launch
 DCS_API double dcs_debug_flat(dcs_handle* h, int mode, int repeats) {
   cudaSetDevice(h->dev);
-  const int grid = cdiv(h->nh, 256);
-  for (int i = 0; i < 3; ++i) k_dbg_flat<<<grid, 256, 0, h->stream>>>(h->h_other.p, h->h_tmx.p, h->h_tmy.p, h->h_thm.p, h->xyt.p, h->nh, h->ldh, h->Hoff.p, mode);
+  const int64_t ns = h->n_slot_tiles * kSlice;
+  const int grid = cdiv(ns, 256);
+  for (int i = 0; i < 3; ++i) k_dbg_flat<<<grid, 256, 0, h->stream>>>(h->recs.p, h->xyt.p, ns, h->Hup.p, h->ldu, mode);
   cudaEventRecord(h->ev0, h->stream);
-  for (int i = 0; i < repeats; ++i) k_dbg_flat<<<grid, 256, 0, h->stream>>>(h->h_other.p, h->h_tmx.p, h->h_tmy.p, h->h_thm.p, h->xyt.p, h->nh, h->ldh, h->Hoff.p, mode);
+  for (int i = 0; i < repeats; ++i) k_dbg_flat<<<grid, 256, 0, h->stream>>>(h->recs.p, h->xyt.p, ns, h->Hup.p, h->ldu, mode);
   cudaEventRecord(h->ev1, h->stream);
   cudaEventSynchronize(h->ev1);
   float ms = 0;
@@ -106,7 +102,7 @@ DCS_API int dcs_debug_pcg_stages(dcs_handle* h, int repeats, double* out6) {
   const double* D = h->Adiag.p;
   for (int it = 0; it < repeats + 3; ++it) {
     cudaEventRecord(ev[0], h->stream);
-    LAUNCH(k_spmv, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->h_other.p, h->Hoff.p, D, h->q.p, h->task_part.p);
+    LAUNCH(k_spmv<double>, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
     k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1, h->fold_ws.p, h->tickets.p + 6);
     cudaEventRecord(ev[1], h->stream);
     CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));

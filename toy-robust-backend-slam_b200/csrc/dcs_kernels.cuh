@@ -20,234 +20,205 @@ namespace dcs {
 
 // scalar slots in the device scalar block
 enum { S_COST = 0, S_GSQ = 1, S_GMAX = 2, S_PQ = 3, S_RZ = 4, S_RZ_NEXT = 5, S_RR = 6, S_RR0 = 7,
-       S_WG = 8, S_WHW = 9, S_STEP_SQ = 10, S_XSQ = 11, S_CAND_COST = 12, S_TMP = 13, S_COUNT = 16 };
+       S_WG = 8, S_WHW = 9, S_STEP_SQ = 10, S_XSQ = 11, S_CAND_COST = 12, S_TMP = 13 /* 13, 14 */, S_TRES = 16, S_COUNT = 24 };
 
-struct RowLayout {           // jagged-diagonal layout of the owned rows
-  int32_t row_lo;            // first owned pose
-  int32_t nrows;             // owned poses
-  int64_t ldn;               // leading dimension of per-row SoA arrays (>= gridDim * kRowsPerBlock)
-  int64_t ldh;               // leading dimension of per-half-edge SoA arrays
-  const int32_t* row_ptr;    // [nrows+1] sorted-CSR offsets (gives the degree)
-  const uint16_t* perm;      // [nwin*kWindow] rank -> local row within the window
-  const int32_t* rp_off;     // [nwin+1] offset of the window's rounds in round_ptr
-  const int32_t* round_ptr;  // first slot of every round
-  int32_t nwin;              // windows of kWindow rows
-  int32_t ntasks;            // nwin * kSlicesPerWindow warp tasks
-  const uint32_t* rank_info; // [nwin*kWindow] rank -> degree << 10 | local row within the window
-  const int32_t* round32;    // [nwin*32] first 32 round starts of every window
-  const uint2* first_words;  // [nwin*kWindow] rank -> half-edge words of rounds 0 and 1 (copies of `other`)
-  const int32_t* task_obase; // [ntasks+1] first compact owner-block index of every task
-  int64_t ldu;               // leading dimension of the compact owner-block SoA (Hup)
+// Sliced-ELL layout of the owned rows (SELL-32 with a 1024-row sorting window).  Rows are ranked by (degree,
+// owner entries) inside their window and STORED in that order; a warp task = 32 consecutive stored rows; the k-th
+// half-edges of a task's rows form one TILE of 32 slots, and a task's tiles are consecutive:
+//     slot(row position m, k) = (tile0[m / 32] + k) * 32 + (m & 31),      tile0 = exclusive scan of the tasks' max degree.
+// Every per-half-edge array is indexed by slot, so a task streams ONE contiguous run per array (no round pointers, no
+// shuffles, constant offsets inside a tile); slots beyond a row's degree are padding (3 % of the slots on the
+// benchmark graph - address space only, inactive lanes never touch them).
+struct RowLayout {
+  int32_t nrows;             // owned poses (stored positions [0, nrows) are real rows)
+  int32_t ntasks;            // 32-row warp tasks (= ldn / 32)
+  int64_t ldn;               // leading dimension of per-row SoA arrays
+  int64_t ldh;               // slots = 32 * (tiles + kTailTiles)
+  int64_t ldu;               // compact owner-block capacity (multiple of 32)
+  const uint4* rowinfo;      // [ldn] per stored row: (degree, word of round 0, word of round 1, 0)
+  const int2* task_info;     // [ntasks + 1] (first tile, first compact owner-block index)
 };
 
-// Warp task mapping shared by the row-owner kernels: CTA = one warp = slice `sl` (ranks [32 sl, 32 sl + 32))
-// of degree-sorted window `win`.  Window-major order keeps concurrently running CTAs on neighbouring rows
-// (their gathered operands overlap in L2); within a window the longest slices start first.
-// The task's start-up needs two independent coalesced loads (rank_info, round32) instead of the chain
-// perm -> row_ptr and rp_off -> round_ptr; `rp` (rounds >= 32, and the kernels that index it directly) is
-// only waited for where it is used.
-struct WarpTask { int lr; int rank; int deg; int rp_lane; const int32_t* rp; bool valid; int64_t slot0; };
-__device__ __forceinline__ WarpTask warp_task(const RowLayout& L) {
-  WarpTask w;
-  const int task = blockIdx.x;
-  w.valid = task < L.ntasks;
-  const int win = w.valid ? task / kSlicesPerWindow : 0;
-  const int sl = w.valid ? task - win * kSlicesPerWindow : 0;
-  const int lane = threadIdx.x & 31;
-  w.rank = sl * kSlice + lane;
-  const int64_t slot0 = (int64_t)win * kWindow;
-  w.slot0 = slot0;
-  const uint32_t info = L.rank_info[slot0 + w.rank];
-  w.rp_lane = L.round32[win * 32 + lane];
-  w.lr = (int)slot0 + w.rank;        // rows are stored in (window, rank) order
-  w.deg = (w.valid && w.lr < L.nrows) ? (int)(info >> 10) : 0;
-  w.rp = L.round_ptr + L.rp_off[win];
-  return w;
+// What k_linearize streams: 32 bytes per half-edge, one 256-bit load per lane, a tile = 1 KB contiguous.
+struct __align__(32) HalfEdgeRec {
+  double tmx, tmy;           // Rm^T (dx, dy), rotated once at upload
+  double thm;                // measured rotation
+  uint32_t word;             // other pose (local index) | flags
+  uint32_t word_next;        // word of the same row kK1Rounds rounds later (0 past the row's end): the gather of the
+                             // next pipeline stage needs no separate index stream
+};
+
+// Tile-interleaved 3x3 block arrays ([tile][9][32], T = double or float): all nine values of a lane's block sit at
+// constant offsets from one address, a warp writes / reads 9 x 256 (128) contiguous bytes of one 2304 (1152)-byte tile.
+__device__ __forceinline__ int64_t block_base(int64_t slot) { return (slot >> 5) * 288 + (slot & 31); }
+
+__device__ __forceinline__ void ld_rec(HalfEdgeRec& r, const HalfEdgeRec* p, uint64_t pol) {
+  uint64_t w;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b64 {%0, %1, %2, %3}, [%4], %5;"
+               : "=d"(r.tmx), "=d"(r.tmy), "=d"(r.thm), "=l"(w) : "l"(p), "l"(pol));
+  r.word = (uint32_t)w; r.word_next = (uint32_t)(w >> 32);
+}
+struct PoseRec { double x, y, th; };
+__device__ __forceinline__ void ld_pose(PoseRec& r, const double4* p, uint64_t pol) {   // one 32-byte sector per gathered pose
+  [[maybe_unused]] double pad;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.th), "=d"(pad) : "l"(p), "l"(pol));
+  (void)pad;
 }
 
-struct HalfEdges {           // per-half-edge SoA, in JDS slot order: 28 B per half-edge
-  const uint32_t* other;     // other pose | flags
-  const double* tmx;         // Rm^T (dx,dy)
-  const double* tmy;
-  const double* thm;
-};
+#ifdef DCS_CHECK
+// -DDCS_CHECK (make check): device-side bounds asserts on every gathered / scattered index of the row-owner kernels
+#define DCS_ASSERT(cond) do { if (!(cond)) { printf("DCS_CHECK failed: %s (%s:%d) block %d lane %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define DCS_ASSERT(cond) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K2
 // ------------------------------------------------------------------------------------------------
-struct HalfEdgeRec { double tmx, tmy, thm; };
-struct PoseRec { double x, y, th; };
-
-__device__ __forceinline__ HalfEdgeRec load_rec(const HalfEdges& H, int64_t idx, uint64_t pol) {
-  HalfEdgeRec r;
-  r.tmx = ld_stream(H.tmx + idx, pol); r.tmy = ld_stream(H.tmy + idx, pol); r.thm = ld_stream(H.thm + idx, pol);
-  return r;
-}
-__device__ __forceinline__ PoseRec gather_pose(const double4* __restrict__ xyt, uint32_t word, uint64_t pol) {
-  const double4 p = ld_keep4(xyt + (word & kIdxMask), pol);     // one 32-byte sector per gathered pose
-  PoseRec r;
-  r.x = p.x; r.y = p.y; r.th = p.z;
-  return r;
-}
-
-// The assembled product is the reference's structure: the upper-triangular block matrix (one 3x3
-// off-diagonal block per edge, written by the half-edge whose row is the smaller endpoint: kFlagOwner),
-// the diagonal blocks and the gradient.  The owner blocks go to a COMPACT array Hup (9 planes of ldu doubles)
-// in (task, round, lane) order: a task writes one dense run per plane, every 32-byte sector and 128-byte
-// line is written whole (partially written lines cost DRAM the same as full ones: the flat traffic probe
-// writes the 288 MB of owner blocks scattered over the slot space in 80 us, all 576 MB of slots in 92 us).
-// The full row storage the SpMV walks (both triangles, slot order) is filled from Hup by k_expand as part
-// of the linear-solver setup.
-// 16 resident one-warp CTAs per SM (128 registers per thread), two rounds per pipeline stage: measured best
-// (profiles/r01_kernels.md lists the other occupancy / depth combinations and the cp.async-ring pipeline).
+// The assembled product is the reference's structure: one 3x3 off-diagonal block per edge (written by the half-edge
+// whose row is the smaller endpoint, or whose partner row lives on another rank: kFlagOwner), the diagonal blocks and
+// the gradient.  The owner blocks go to a COMPACT tile-interleaved array Hup in (task, round, lane) order - a task
+// writes one dense run, every sector / line is written whole (partially written lines cost DRAM the same as full
+// ones) - always in the edge's own orientation H_ab = J_a^T J_b (row a, column b), whichever endpoint owns it: no
+// per-value selects; consumers transpose where their row is the b endpoint.
+//
+// Pipeline: one warp per task, kK1Rounds rounds per stage, registers only.  ptxas tracks every long-latency load of
+// the loop on one scoreboard, so the stage is in lockstep: next stage's records and gathered poses are issued at the
+// top (the gather addresses come from the CURRENT records' word_next), the current stage's math runs on registers
+// that hold no pending load, and the stage ends with the only scoreboard wait.  The two register sets swap roles by
+// unrolling two stages (no rotation moves); prefetch tile indices are clamped to the task's last tile (no
+// predication, a re-read of that tile hits L2).
 #ifndef DCS_K1_WARPS
 #define DCS_K1_WARPS 16
 #endif
-#ifndef DCS_K1_ROUNDS     // rounds fetched and processed per pipeline stage (1 or 2)
-#define DCS_K1_ROUNDS 2
+#ifndef DCS_K1_PF_OWN
+#define DCS_K1_PF_OWN 1
 #endif
+#ifndef DCS_K1_PF_AHEAD
+#define DCS_K1_PF_AHEAD 0
+#endif
+struct K1Stage { HalfEdgeRec rec[kK1Rounds]; PoseRec pose[kK1Rounds]; };
+
 __global__ void __launch_bounds__(kRowsPerBlock, DCS_K1_WARPS)
-k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
-            double* __restrict__ Hup, double* __restrict__ Hdiag, double* __restrict__ grad,
-            double* __restrict__ task_part) {
+k_linearize(const double4* __restrict__ xyt, RowLayout L, const HalfEdgeRec* __restrict__ recs, Params P, int32_t n_loc,
+            double* __restrict__ Hup, double* __restrict__ Hdiag, double* __restrict__ grad, double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
-  // What a task needs to start: four independent coalesced words per lane.
-  struct TaskWords { uint32_t info; int rp_lane; uint2 fw; int obase; };
-  auto load_task_words = [&](int task) {
-    TaskWords w;
-    const int win = task / kSlicesPerWindow, sl = task - win * kSlicesPerWindow;
-    const int lane_ = threadIdx.x & 31;
-    const int64_t i = (int64_t)win * kWindow + sl * kSlice + lane_;
-    w.info = L.rank_info[i];
-    w.rp_lane = L.round32[win * 32 + lane_];
-    w.fw = L.first_words[i];                       // words of rounds 0 and 1: the first gathers need no word load
-    w.obase = L.task_obase[task];
-    return w;
-  };
-  // (Persistent warps with next-task prefetch were measured: 261 us instead of 191 - static task striding loses the
-  // hardware scheduler's load balance and the L1/L2 locality of neighbouring tasks.)
+  constexpr int kR = kK1Rounds;
   const int task = blockIdx.x;
   if (task >= L.ntasks) return;
-  const TaskWords tw = load_task_words(task);
-  const int win = task / kSlicesPerWindow;
-  const int t = (task - win * kSlicesPerWindow) * kSlice + (threadIdx.x & 31);   // rank inside the window
-  const int lr = win * kWindow + t;                 // rows are stored in (window, rank) order: coalesced row arrays
-  const bool has_row = lr < L.nrows;
-  int orun = tw.obase;                              // compact index of the task's next owner block
-  const uint2 fw = tw.fw;
-  int deg = 0;
-  double ox = 0, oy = 0, oth = 0;
-  if (has_row) {
-    deg = (int)(tw.info >> 10);
-    const double4 p = ld_keep4(xyt + L.row_lo + lr, pol.keep);
-    ox = p.x; oy = p.y; oth = p.z;
+  const int lane = threadIdx.x & 31;
+  const int lr = task * kSlice + lane;              // rows are stored in task order: coalesced row arrays
+  // start-up: three independent coalesced loads, then the first records + gathers
+  const uint4 info = L.rowinfo[lr];
+  const int2 ti = L.task_info[task];
+  PoseRec own;
+  ld_pose(own, xyt + lr, pol.keep);
+  const int deg = lr < L.nrows ? (int)info.x : 0;
+  const int kmax = __reduce_max_sync(0xffffffffu, deg);
+  const HalfEdgeRec* rp = recs + (int64_t)ti.x * kSlice + lane;     // this lane's record of round 0; round k: + k * 32
+  int orun = ti.y;                                  // compact index of the task's next owner block
+  // Bulk L2 prefetches (one instruction by one lane, no destination register, no scoreboard):
+  //  * DCS_K1_PF_OWN: the task's own record run is ONE contiguous range (kmax KB) - start its DRAM fetch now so the
+  //    pipeline's record loads find their lines in L2;
+  //  * DCS_K1_PF_AHEAD = G > 0: everything task + G will read at its start-up and stream afterwards (its row infos,
+  //    own poses and record run are contiguous ranges too).  G ~ the number of resident tasks, i.e. the task that
+  //    starts when this one ends: every task then starts from L2 instead of paying two DRAM latencies in series.
+  constexpr int kPrefetchTiles = 32;
+#if DCS_K1_PF_OWN
+  if (lane == 0 && kmax > kR)
+    prefetch_l2_bulk(recs + ((int64_t)ti.x + kR) * kSlice, (uint32_t)(min(kmax - kR, kPrefetchTiles) * kSlice * (int)sizeof(HalfEdgeRec)));
+#endif
+#if DCS_K1_PF_AHEAD > 0
+  const int tf = task + DCS_K1_PF_AHEAD;
+  int2 tif = make_int2(0, 0), tif1 = make_int2(0, 0);
+  if (tf < L.ntasks) {                              // warp-uniform
+    tif = L.task_info[tf]; tif1 = L.task_info[tf + 1];
+    if (lane == 0) {
+      prefetch_l2_bulk(L.rowinfo + (int64_t)tf * kSlice, kSlice * (int)sizeof(uint4));
+      prefetch_l2_bulk(xyt + (int64_t)tf * kSlice, kSlice * (int)sizeof(double4));
+    }
   }
+#endif
   double d00 = 0, d01 = 0, d02 = 0, d11 = 0, d12 = 0, d22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
 
-  auto process = [&](uint32_t word, const HalfEdgeRec& r, const PoseRec& pc, int64_t idx) {
-    const bool side_b = (word & kFlagSideB) != 0;
-    // edge frame: a = first endpoint, b = second
-    const double xa = side_b ? pc.x : ox, ya = side_b ? pc.y : oy, tha = side_b ? pc.th : oth;
-    const double xb = side_b ? ox : pc.x, yb = side_b ? oy : pc.y, thb = side_b ? oth : pc.th;
-    EdgeTerms T;
-    edge_terms(xa, ya, tha, xb, yb, thb, r.tmx, r.tmy, r.thm, (word & kFlagDcs) != 0, P, T);
-    // diagonal block of the row pose and its gradient, accumulated in slot order
-    d00 += T.U00; d01 += T.U01; d11 += T.U11;
-    d02 += side_b ? T.sc0 : -T.e0;
-    d12 += side_b ? T.sc1 : -T.e1;
-    d22 += side_b ? T.alpha : T.k22;
-    g0 += side_b ? T.bf0 : -T.bf0;
-    g1 += side_b ? T.bf1 : -T.bf1;
-    g2 += side_b ? T.gb : T.ga;
-    if (word & kFlagCost) cost += T.cost;
-    if (word & kFlagOwner) {   // off-diagonal block (row pose x other pose)
-      double* out = Hup + idx;
-      st_stream(out + 0 * L.ldu, -T.U00, pol.stream);
-      st_stream(out + 1 * L.ldu, -T.U01, pol.stream);
-      st_stream(out + 2 * L.ldu, side_b ? T.e0 : -T.sc0, pol.stream);
-      st_stream(out + 3 * L.ldu, -T.U01, pol.stream);
-      st_stream(out + 4 * L.ldu, -T.U11, pol.stream);
-      st_stream(out + 5 * L.ldu, side_b ? T.e1 : -T.sc1, pol.stream);
-      st_stream(out + 6 * L.ldu, side_b ? -T.sc0 : T.e0, pol.stream);
-      st_stream(out + 7 * L.ldu, side_b ? -T.sc1 : T.e1, pol.stream);
-      st_stream(out + 8 * L.ldu, T.o22, pol.stream);
+  auto process = [&](const HalfEdgeRec& r, const PoseRec& pc, bool on) {
+    const uint32_t word = r.word;
+    const unsigned om = __ballot_sync(0xffffffffu, on && (word & kFlagOwner));
+    if (on) {
+      const EdgeFrame F = edge_frame(own.x, own.y, own.th, pc.x, pc.y, pc.th, word);
+      const EdgeCore C = edge_core(F, r.tmx, r.tmy, r.thm, (word & kFlagDcs) != 0, P);
+      EdgeTerms T;
+      edge_terms(F, C, T);
+      // diagonal block of the row pose and its gradient, accumulated in slot order
+      d00 += T.U00; d01 += T.U01; d11 += T.U11;
+      if (word & kFlagSideB) { d02 += T.sc0; d12 += T.sc1; d22 += T.alpha; g0 += T.bf0; g1 += T.bf1; g2 += T.gb; }
+      else                   { d02 -= T.e0;  d12 -= T.e1;  d22 += T.k22;   g0 -= T.bf0; g1 -= T.bf1; g2 += T.ga; }
+      if (word & kFlagCost) cost += T.cost;
+      if (word & kFlagOwner) {   // H_ab, edge orientation
+        const int64_t idx = (int64_t)orun + __popc(om & ((1u << lane) - 1u));
+        DCS_ASSERT(idx >= 0 && idx < L.ldu);
+        double* out = Hup + block_base(idx);
+        st_stream(out + 0 * 32, -T.U00, pol.stream);
+        st_stream(out + 1 * 32, -T.U01, pol.stream);
+        st_stream(out + 2 * 32, -T.sc0, pol.stream);
+        st_stream(out + 3 * 32, -T.U01, pol.stream);
+        st_stream(out + 4 * 32, -T.U11, pol.stream);
+        st_stream(out + 5 * 32, -T.sc1, pol.stream);
+        st_stream(out + 6 * 32, T.e0, pol.stream);
+        st_stream(out + 7 * 32, T.e1, pol.stream);
+        st_stream(out + 8 * 32, T.o22, pol.stream);
+      }
+    }
+    orun += __popc(om);
+  };
+  // loads of the kR rounds starting at round k into stage S; the gather indices are `words`
+  auto fetch = [&](K1Stage& S, int k, const uint32_t (&words)[kR]) {
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      const int kk = min(k + u, kmax - 1);          // clamp: past the task's end re-read its last tile (unused)
+      ld_rec(S.rec[u], rp + (int64_t)kk * kSlice, pol.stream);
+    }
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      const uint32_t j = words[u] & kIdxMask;
+      DCS_ASSERT((int32_t)j < n_loc);
+      ld_pose(S.pose[u], xyt + j, pol.keep);
     }
   };
+  auto next_words = [&](const K1Stage& S, uint32_t (&words)[kR]) {
+#pragma unroll
+    for (int u = 0; u < kR; ++u) words[u] = S.rec[u].word_next;
+  };
 
-  // Software pipeline in registers, one round deep and in lockstep.  ptxas tracks every long-latency load of
-  // this loop on ONE scoreboard, so a wait for any loaded value also waits for every load issued before it:
-  // the loads of round k+1 (record, gathered pose, index word of round k+2) are therefore issued at the top of
-  // round k, the round-k math then runs entirely on registers that hold no pending load, and the only
-  // scoreboard wait of the loop is the rotation next -> current at its end.  For the same reason nothing is
-  // re-loaded inside the loop (lane i keeps the start of round i, a shuffle hands it out), the loop is
-  // warp-uniform, and the loads are predicated instructions rather than branches.
-  // kR rounds are fetched and processed per pipeline stage: more bytes in flight per warp and kR rounds of
-  // arithmetic to cover them, at the price of kR sets of staging registers (kR = 2 needs 128 registers/thread).
-  constexpr int kR = DCS_K1_ROUNDS;
-  const int lane = threadIdx.x & 31;
-  const int kmax = __reduce_max_sync(0xffffffffu, deg);
-  for (int base = 0; base < kmax; base += 32) {
-    const int kend = min(kmax, base + 32);
-    const int dend = min(deg, kend);                 // this lane's rounds of the chunk end here
-    const int rpreg = base == 0 ? tw.rp_lane : ((base + lane < kend) ? (L.round_ptr + L.rp_off[win])[base + lane] : 0);
-    auto slot_of = [&](int k) -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, rpreg, k & 31) + t; };
-    uint32_t wC[kR], wN[kR], wNN[kR];
-    HalfEdgeRec recC[kR], recN[kR];
-    PoseRec poseC[kR], poseN[kR];
-    int64_t sN[kR];
-#pragma unroll
-    for (int u = 0; u < kR; ++u) {
-      wC[u] = wN[u] = wNN[u] = 0u;
-      recC[u] = recN[u] = HalfEdgeRec{0, 0, 0};
-      poseC[u] = poseN[u] = PoseRec{0, 0, 0};
-    }
-    static_assert(kR <= 2, "first_words holds two rounds");
-#pragma unroll
-    for (int u = 0; u < kR; ++u) {
-      const int64_t sC = slot_of(base + u);
-      const bool on = base + u < dend;
-      if (base == 0) wC[u] = on ? (u == 0 ? fw.x : fw.y) : 0u;
-      else ld_stream_u32_if(wC[u], H.other + sC, pol.stream, on);
-      ld_stream_if(recC[u].tmx, H.tmx + sC, pol.stream, on);
-      ld_stream_if(recC[u].tmy, H.tmy + sC, pol.stream, on);
-      ld_stream_if(recC[u].thm, H.thm + sC, pol.stream, on);
-    }
-#pragma unroll
-    for (int u = 0; u < kR; ++u) {
-      sN[u] = slot_of(base + kR + u);
-      ld_stream_u32_if(wN[u], H.other + sN[u], pol.stream, base + kR + u < dend);
-    }
-#pragma unroll
-    for (int u = 0; u < kR; ++u)
-      ld_keep3_if(poseC[u].x, poseC[u].y, poseC[u].th, xyt + (wC[u] & kIdxMask), pol.keep, base + u < dend);
+  if (kmax > 0) {
+    static_assert(kR == 2, "rowinfo carries the words of two rounds");
+    K1Stage A, B;
+    uint32_t w[kR] = {info.y, info.z};
+    fetch(A, 0, w);
 #pragma unroll 1
-    for (int k = base; k < kend; k += kR) {
+    for (int k = 0; k < kmax; k += 2 * kR) {
+#if DCS_K1_PF_OWN
+      if (lane == 0 && k > 0 && (k % kPrefetchTiles) == 0 && k + kR + kPrefetchTiles / 2 < kmax)    // long rows only
+        prefetch_l2_bulk(recs + ((int64_t)ti.x + k + kR + kPrefetchTiles / 2) * kSlice,
+                         (uint32_t)(min(kmax - (k + kR + kPrefetchTiles / 2), kPrefetchTiles) * kSlice * (int)sizeof(HalfEdgeRec)));
+#endif
+      next_words(A, w);
+      fetch(B, k + kR, w);
 #pragma unroll
-      for (int u = 0; u < kR; ++u) {
-        const bool on1 = k + kR + u < dend;
-        ld_stream_if(recN[u].tmx, H.tmx + sN[u], pol.stream, on1);
-        ld_stream_if(recN[u].tmy, H.tmy + sN[u], pol.stream, on1);
-        ld_stream_if(recN[u].thm, H.thm + sN[u], pol.stream, on1);
-        ld_keep3_if(poseN[u].x, poseN[u].y, poseN[u].th, xyt + (wN[u] & kIdxMask), pol.keep, on1);
-      }
-      int64_t sNN[kR];
+      for (int u = 0; u < kR; ++u) process(A.rec[u], A.pose[u], k + u < deg);
+      if (k + kR >= kmax) break;
+      next_words(B, w);
+      fetch(A, k + 2 * kR, w);
 #pragma unroll
-      for (int u = 0; u < kR; ++u) {
-        sNN[u] = slot_of(k + 2 * kR + u);
-        ld_stream_u32_if(wNN[u], H.other + sNN[u], pol.stream, k + 2 * kR + u < dend);
-      }
-#pragma unroll
-      for (int u = 0; u < kR; ++u) {
-        const bool on = k + u < dend;
-        const unsigned om = __ballot_sync(0xffffffffu, on && (wC[u] & kFlagOwner));
-        if (on) process(wC[u], recC[u], poseC[u], (int64_t)orun + __popc(om & ((1u << lane) - 1u)));
-        orun += __popc(om);
-      }
-#pragma unroll
-      for (int u = 0; u < kR; ++u) { wC[u] = wN[u]; wN[u] = wNN[u]; recC[u] = recN[u]; poseC[u] = poseN[u]; sN[u] = sNN[u]; }
+      for (int u = 0; u < kR; ++u) process(B.rec[u], B.pose[u], k + kR + u < deg);
     }
   }
-  if (has_row) {
+#if DCS_K1_PF_AHEAD > 0
+  if (lane == 0 && tf < L.ntasks && tif1.x > tif.x)     // the future task's record run (first kPrefetchTiles tiles)
+    prefetch_l2_bulk(recs + (int64_t)tif.x * kSlice, (uint32_t)(min(tif1.x - tif.x, kPrefetchTiles) * kSlice * (int)sizeof(HalfEdgeRec)));
+#endif
+  if (lr < L.nrows) {
     Hdiag[0 * L.ldn + lr] = d00; Hdiag[1 * L.ldn + lr] = d01; Hdiag[2 * L.ldn + lr] = d02;
     Hdiag[3 * L.ldn + lr] = d11; Hdiag[4 * L.ldn + lr] = d12; Hdiag[5 * L.ldn + lr] = d22;
     grad[0 * L.ldn + lr] = g0; grad[1 * L.ldn + lr] = g1; grad[2 * L.ldn + lr] = g2;
@@ -261,7 +232,7 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P,
     r1 += __shfl_xor_sync(0xffffffffu, r1, o);
     r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     const size_t n = L.ntasks;
     task_part[task] = r0; task_part[n + task] = r1; task_part[2 * n + task] = r2;
   }
@@ -347,73 +318,84 @@ k_fold_tasks(const double* __restrict__ part, int n, double* out, double* scal, 
   }
 }
 
-// Pattern build: enumerate the owner half-edges exactly as k_linearize meets them (task, round, lane).
-// kWrite = false: own_cnt[task] = owner half-edges of the task; kWrite = true: cidx[slot] = compact index.
+// Pattern build, one warp per task walking its tiles exactly as k_linearize does.
+//   kWrite = false: own_cnt[task] = owner half-edges of the task (scanned into the compact base of every task)
+//   kWrite = true : cidx[slot] = compact owner-block index in (task, round, lane) order; the records' word_next
+//                   (word of the same row kK1Rounds rounds later); rowinfo (degree + the words of rounds 0 and 1)
 template <bool kWrite>
 __global__ void __launch_bounds__(kRowsPerBlock)
-k_owner_enum(RowLayout L, const uint32_t* __restrict__ other, int32_t* own_cnt, int32_t* cidx) {
-  const WarpTask wt = warp_task(L);
-  const int lane = threadIdx.x & 31;
-  const int deg = wt.deg;
+k_task_walk(int32_t ntasks, const uint32_t* __restrict__ rank_info, const int32_t* __restrict__ tile0, const int32_t* __restrict__ obase,
+            const uint32_t* __restrict__ cols, int32_t* own_cnt, int32_t* cidx, HalfEdgeRec* recs, uint4* rowinfo) {
+  const int task = blockIdx.x, lane = threadIdx.x & 31;
+  if (task >= ntasks) return;
+  const int m = task * kSlice + lane;
+  const int deg = (int)(rank_info[m] >> 10);
   const int kmax = __reduce_max_sync(0xffffffffu, deg);
-  int run = (kWrite && wt.valid) ? L.task_obase[blockIdx.x] : 0;
+  const int64_t s0 = (int64_t)tile0[task] * kSlice + lane;
+  int run = kWrite ? obase[task] : 0;
   for (int k = 0; k < kmax; ++k) {
-    const int64_t s = (int64_t)wt.rp[k] + wt.rank;
-    const bool own = k < deg && (other[s] & kFlagOwner);
+    const int64_t s = s0 + (int64_t)k * kSlice;
+    const bool own = k < deg && (cols[s] & kFlagOwner);
     const unsigned om = __ballot_sync(0xffffffffu, own);
-    if (kWrite && own) cidx[s] = run + __popc(om & ((1u << lane) - 1u));
+    if (kWrite) {
+      if (own) cidx[s] = run + __popc(om & ((1u << lane) - 1u));
+      if (k < deg) recs[s].word_next = (k + kK1Rounds < deg) ? cols[s + (int64_t)kK1Rounds * kSlice] : 0u;
+    }
     run += __popc(om);
   }
-  if (!kWrite && lane == 0 && wt.valid) own_cnt[blockIdx.x] = run;
+  if (kWrite) rowinfo[m] = make_uint4((uint32_t)deg, deg > 0 ? cols[s0] : 0u, deg > 1 ? cols[s0 + kSlice] : 0u, 0u);
+  else if (lane == 0) own_cnt[task] = run;
+}
+__global__ void k_task_kmax(int32_t ntasks, const uint32_t* __restrict__ rank_info, int32_t* kmax) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntasks) kmax[t] = (int32_t)(rank_info[(int64_t)t * kSlice] >> 10);     // ranks are degree-sorted: the first lane has the most
+}
+__global__ void k_task_info(int32_t ntasks, const int32_t* __restrict__ tile0, const int32_t* __restrict__ obase, int2* task_info) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= ntasks) task_info[t] = make_int2(tile0[t], obase[t]);
 }
 
-// first_words[window][rank] = the rank's half-edge words of rounds 0 and 1
-__global__ void k_first_words(RowLayout L, const uint32_t* __restrict__ other, uint2* first_words) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)L.nwin * kWindow) return;
-  const int win = (int)(i / kWindow), rank = (int)(i % kWindow);
-  const int deg = (int)(L.rank_info[i] >> 10);
-  uint2 w = make_uint2(0u, 0u);
-  if (deg > 0) w.x = other[(int64_t)L.round32[win * 32 + 0] + rank];
-  if (deg > 1) w.y = other[(int64_t)L.round32[win * 32 + 1] + rank];
-  first_words[i] = w;
-}
-
-// expand_src[slot]: >= 0 copy compact block, <= -2 transpose compact block (-2 - src), -1 no block
-__global__ void k_expand_src(const uint32_t* __restrict__ other, const int32_t* __restrict__ mirror_src,
-                             const int32_t* __restrict__ cidx, int32_t nh, int32_t* expand_src) {
-  const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nh) return;
-  int32_t src = -1;
-  if (other[s] & kFlagOwner) src = cidx[s];
-  else if (mirror_src[s] >= 0) src = -2 - cidx[mirror_src[s]];
-  expand_src[s] = src;
-}
-
-// Linear-solver setup: the SpMV walks full rows in slot order, so every slot receives its block from the
-// compact upper-triangular array: owner slots a copy, their partners the transpose, the rest zero.
-__global__ void k_expand(const int32_t* __restrict__ expand_src, int32_t nh, int64_t ldh, int64_t ldu,
-                         const double* __restrict__ Hup, double* __restrict__ Hoff) {
+// block_src[slot]: compact index of the slot's edge block (its own if the slot is an owner, its partner's otherwise),
+// -1 when the edge has no off-diagonal block (other endpoint constant)
+__global__ void k_block_src(const uint32_t* __restrict__ cols, const int32_t* __restrict__ slot, const int32_t* __restrict__ mirror_src,
+                            const int32_t* __restrict__ cidx, int32_t nh, int32_t* block_src) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
-  const int32_t s = expand_src[i];
+  const int32_t s = slot[i];
+  int32_t src = -1;
+  if (cols[s] & kFlagOwner) src = cidx[s];
+  else if (mirror_src[s] >= 0) src = cidx[mirror_src[s]];
+  block_src[s] = src;
+}
+
+// Linear-solver setup: the SpMV walks full rows in slot order, so every slot receives its block from the compact
+// array of edge blocks H_ab: slots whose row is the a endpoint a copy, b-endpoint slots the transpose, the rest
+// (padding, constant partner) zero.  T = double (the operator of the linear system) or float (its single-precision
+// shadow for the mixed-precision inner iterations).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_expand(const int32_t* __restrict__ block_src, const uint32_t* __restrict__ cols, int64_t nslots, const double* __restrict__ Hup,
+         T* __restrict__ Hoff) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  const int32_t s = block_src[i];
   double v[9];
-  if (s == -1) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) v[c] = 0.0;
-  } else {
-    const int64_t j = s >= 0 ? s : -2 - s;
+  for (int c = 0; c < 9; ++c) v[c] = 0.0;
+  if (s >= 0) {
+    const double* in = Hup + block_base(s);
 #pragma unroll
-    for (int c = 0; c < 9; ++c) v[c] = Hup[(int64_t)c * ldu + j];
+    for (int c = 0; c < 9; ++c) v[c] = in[c * 32];
   }
-  if (s >= -1) {
+  T* out = Hoff + block_base(i);
+  if (!(cols[i] & kFlagSideB)) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) Hoff[(int64_t)c * ldh + i] = v[c];
+    for (int c = 0; c < 9; ++c) out[c * 32] = (T)v[c];
   } else {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) Hoff[(int64_t)(3 * r + c) * ldh + i] = v[3 * c + r];
+      for (int c = 0; c < 3; ++c) out[(3 * r + c) * 32] = (T)v[3 * c + r];
   }
 }
 
@@ -435,32 +417,45 @@ constexpr int kEdgeThreads = 256;
 // K6: cost at a candidate point over the rank's own rows: every edge is booked on exactly one half-edge
 // (kFlagCost), so each rank needs only its own + halo poses and the ranks' partial costs add up.
 __global__ void __launch_bounds__(kRowsPerBlock)
-k_cost_rows(const double4* __restrict__ xyt, RowLayout L, HalfEdges H, Params P, double* __restrict__ task_part) {
+k_cost_rows(const double4* __restrict__ xyt, RowLayout L, const HalfEdgeRec* __restrict__ recs, Params P, int32_t n_loc,
+            double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
-  const WarpTask wt = warp_task(L);
-  const int t = wt.rank;
-  const int lr = wt.lr;
+  const int task = blockIdx.x, lane = threadIdx.x & 31;
+  if (task >= L.ntasks) return;
+  const int lr = task * kSlice + lane;
   double cost = 0.0;
-  if (wt.valid && lr < L.nrows) {
-    const int deg = wt.deg;
-    const double4 po = ld_keep4(xyt + L.row_lo + lr, pol.keep);
-    for (int k = 0; k < deg; ++k) {
-      const int64_t idx = (int64_t)wt.rp[k] + t;
-      const uint32_t word = ld_stream_u32(H.other + idx, pol.stream);
-      if (!(word & kFlagCost)) continue;
-      const double4 pj = ld_keep4(xyt + (word & kIdxMask), pol.keep);
-      const bool side_b = (word & kFlagSideB) != 0;
-      const double xa = side_b ? pj.x : po.x, ya = side_b ? pj.y : po.y, tha = side_b ? pj.z : po.z;
-      const double xb = side_b ? po.x : pj.x, yb = side_b ? po.y : pj.y, thb = side_b ? po.z : pj.z;
-      double q00, q01, dxw, dyw, epx, epy, ex, ey, eth, sigma, psi2, inv_den, e2, rho1;
-      cost += edge_cost_terms(xa, ya, tha, xb, yb, thb, ld_stream(H.tmx + idx, pol.stream), ld_stream(H.tmy + idx, pol.stream),
-                              ld_stream(H.thm + idx, pol.stream), (word & kFlagDcs) != 0, P, q00, q01, dxw, dyw, epx, epy, ex, ey,
-                              eth, sigma, psi2, inv_den, e2, rho1);
+  if (lr < L.nrows) {
+    const int deg = (int)L.rowinfo[lr].x;
+    PoseRec own;
+    ld_pose(own, xyt + lr, pol.keep);
+    const HalfEdgeRec* rp = recs + (int64_t)L.task_info[task].x * kSlice + lane;
+    constexpr int U = 2;
+    int k = 0;
+    for (; k + U <= deg; k += U) {
+      HalfEdgeRec r[U]; PoseRec pj[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ld_rec(r[u], rp + (int64_t)(k + u) * kSlice, pol.stream);
+#pragma unroll
+      for (int u = 0; u < U; ++u) { DCS_ASSERT((int32_t)(r[u].word & kIdxMask) < n_loc); ld_pose(pj[u], xyt + (r[u].word & kIdxMask), pol.keep); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!(r[u].word & kFlagCost)) continue;
+        const EdgeFrame F = edge_frame(own.x, own.y, own.th, pj[u].x, pj[u].y, pj[u].th, r[u].word);
+        cost += edge_core(F, r[u].tmx, r[u].tmy, r[u].thm, (r[u].word & kFlagDcs) != 0, P).cost;
+      }
+    }
+    for (; k < deg; ++k) {
+      HalfEdgeRec r; PoseRec pj;
+      ld_rec(r, rp + (int64_t)k * kSlice, pol.stream);
+      if (!(r.word & kFlagCost)) continue;
+      ld_pose(pj, xyt + (r.word & kIdxMask), pol.keep);
+      const EdgeFrame F = edge_frame(own.x, own.y, own.th, pj.x, pj.y, pj.th, r.word);
+      cost += edge_core(F, r.tmx, r.tmy, r.thm, (r.word & kFlagDcs) != 0, P).cost;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-  if ((threadIdx.x & 31) == 0) task_part[blockIdx.x] = cost;
+  if (lane == 0) task_part[task] = cost;
 }
 
 __global__ void __launch_bounds__(kEdgeThreads)
@@ -563,39 +558,49 @@ __global__ void k_precond(const double* __restrict__ Hdiag, const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: q = A p (A = diag blocks `D` + off-diagonal blocks), fused p.q; thread per row, JDS layout.
-// `rotate_rz`: fold the PCG scalar rotation S_RZ <- S_RZ_NEXT into the finalising thread (this
-// kernel never reads either, so there is no hazard).
+// K3: q = A p (A = diagonal blocks `D` + the slot-order off-diagonal blocks), fused p.q; thread per row over the
+// SELL tiles: per round a warp reads 128 B of column words and 9 x 256 B (fp64) / 9 x 128 B (fp32 shadow) of one
+// block tile.  T = double: the operator itself; T = float: mixed-precision inner iterations (fp64 vectors and
+// accumulation, single-precision off-diagonal blocks).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_blockval(const double* p, uint64_t pol) { return ld_stream(p, pol); }
+__device__ __forceinline__ double ld_blockval(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return (double)v;
+}
+template <typename T>
 __global__ void __launch_bounds__(kRowsPerBlock)
-k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__ other, const double* __restrict__ Hoff,
-       const double* __restrict__ D, double* __restrict__ q, double* __restrict__ task_part) {
+k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__ cols, const T* __restrict__ Hoff,
+       const double* __restrict__ D, int32_t n_loc, double* __restrict__ q, double* __restrict__ task_part) {
   const L2Policy pol = make_l2_policy();
-  const WarpTask wt = warp_task(L);
-  const int t = wt.rank;
-  const int lr = wt.lr;
+  const int task = blockIdx.x, lane = threadIdx.x & 31;
+  if (task >= L.ntasks) return;
+  const int lr = task * kSlice + lane;
   double y0 = 0, y1 = 0, y2 = 0, dot = 0;
-  if (wt.valid && lr < L.nrows) {
-    const int deg = wt.deg;
-    const double4 p = ld_keep4(p4 + L.row_lo + lr, pol.keep);
+  if (lr < L.nrows) {
+    const int deg = (int)L.rowinfo[lr].x;
+    const int64_t tile0 = L.task_info[task].x;
+    const double4 p = ld_keep4(p4 + lr, pol.keep);
     const double a00 = D[0 * L.ldn + lr], a01 = D[1 * L.ldn + lr], a02 = D[2 * L.ldn + lr];
     const double a11 = D[3 * L.ldn + lr], a12 = D[4 * L.ldn + lr], a22 = D[5 * L.ldn + lr];
     y0 = fma(a00, p.x, fma(a01, p.y, a02 * p.z));
     y1 = fma(a01, p.x, fma(a11, p.y, a12 * p.z));
     y2 = fma(a02, p.x, fma(a12, p.y, a22 * p.z));
-    const int32_t* rp = wt.rp;
+    const uint32_t* cp = cols + tile0 * kSlice + lane;       // round k: + 32 k
+    const T* hp = Hoff + tile0 * 288 + lane;                 // round k: + 288 k, value c: + 32 c
     constexpr int U = 4;     // rounds in flight per thread: 4 x (9 block words + column + gathered p) loads
     int k = 0;
     for (; k + U <= deg; k += U) {
-      int64_t idx[U]; uint32_t j[U]; double h[U][9]; double4 pj[U];
+      uint32_t j[U]; double h[U][9]; double4 pj[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) { idx[u] = (int64_t)rp[k + u] + t; j[u] = ld_stream_u32(other + idx[u], pol.stream) & kIdxMask; }
+      for (int u = 0; u < U; ++u) j[u] = ld_stream_u32(cp + (int64_t)(k + u) * kSlice, pol.stream) & kIdxMask;
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int c = 0; c < 9; ++c) h[u][c] = ld_stream(Hoff + idx[u] + c * L.ldh, pol.stream);
+        for (int c = 0; c < 9; ++c) h[u][c] = ld_blockval(hp + (int64_t)(k + u) * 288 + c * 32, pol.stream);
 #pragma unroll
-      for (int u = 0; u < U; ++u) pj[u] = ld_keep4(p4 + j[u], pol.keep);
+      for (int u = 0; u < U; ++u) { DCS_ASSERT((int32_t)j[u] < n_loc); pj[u] = ld_keep4(p4 + j[u], pol.keep); }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         y0 = fma(h[u][0], pj[u].x, fma(h[u][1], pj[u].y, fma(h[u][2], pj[u].z, y0)));
@@ -604,24 +609,22 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
       }
     }
     for (; k < deg; ++k) {
-      const int64_t idx = (int64_t)rp[k] + t;
-      const uint32_t j = ld_stream_u32(other + idx, pol.stream) & kIdxMask;
-      const double* h = Hoff + idx;
-      const uint64_t ps = pol.stream;
-      const double h0 = ld_stream(h + 0 * L.ldh, ps), h1 = ld_stream(h + 1 * L.ldh, ps), h2 = ld_stream(h + 2 * L.ldh, ps);
-      const double h3 = ld_stream(h + 3 * L.ldh, ps), h4 = ld_stream(h + 4 * L.ldh, ps), h5 = ld_stream(h + 5 * L.ldh, ps);
-      const double h6 = ld_stream(h + 6 * L.ldh, ps), h7 = ld_stream(h + 7 * L.ldh, ps), h8 = ld_stream(h + 8 * L.ldh, ps);
+      const uint32_t j = ld_stream_u32(cp + (int64_t)k * kSlice, pol.stream) & kIdxMask;
+      double h[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) h[c] = ld_blockval(hp + (int64_t)k * 288 + c * 32, pol.stream);
+      DCS_ASSERT((int32_t)j < n_loc);
       const double4 pj = ld_keep4(p4 + j, pol.keep);
-      y0 = fma(h0, pj.x, fma(h1, pj.y, fma(h2, pj.z, y0)));
-      y1 = fma(h3, pj.x, fma(h4, pj.y, fma(h5, pj.z, y1)));
-      y2 = fma(h6, pj.x, fma(h7, pj.y, fma(h8, pj.z, y2)));
+      y0 = fma(h[0], pj.x, fma(h[1], pj.y, fma(h[2], pj.z, y0)));
+      y1 = fma(h[3], pj.x, fma(h[4], pj.y, fma(h[5], pj.z, y1)));
+      y2 = fma(h[6], pj.x, fma(h[7], pj.y, fma(h[8], pj.z, y2)));
     }
     q[0 * L.ldn + lr] = y0; q[1 * L.ldn + lr] = y1; q[2 * L.ldn + lr] = y2;
     dot = fma(p.x, y0, fma(p.y, y1, p.z * y2));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if ((threadIdx.x & 31) == 0) task_part[blockIdx.x] = dot;
+  if (lane == 0) task_part[task] = dot;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -728,8 +731,9 @@ __device__ __forceinline__ void sym3_inverse(double a00, double a01, double a02,
 }
 
 // factorisation: S_0 = D_0; L_j = E_{j-1}^T S_{j-1}^-1; S_j = D_j - L_j E_{j-1}   (E_{j-1} = A[j-1, j])
+template <typename T>
 __global__ void __launch_bounds__(32)
-k_chain_factor(const double* __restrict__ Adiag, const double* __restrict__ Hoff, const int32_t* __restrict__ slot,
+k_chain_factor(const double* __restrict__ Adiag, const T* __restrict__ Hoff, const int32_t* __restrict__ slot,
                const int32_t* __restrict__ chain_idx, const int32_t* __restrict__ chain_cnt, const uint16_t* __restrict__ rank_of,
                int32_t nrows, int64_t ldn, int64_t ldh, float* __restrict__ chL, float* __restrict__ chS) {
   const int lane = threadIdx.x;
@@ -751,7 +755,7 @@ k_chain_factor(const double* __restrict__ Adiag, const double* __restrict__ Hoff
       for (int32_t d = 0; d < cc; ++d) {
         const int64_t sl = slot[ci + d];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) E[c] += Hoff[(int64_t)c * ldh + sl];
+        for (int c = 0; c < 9; ++c) E[c] += (double)Hoff[block_base(sl) + c * 32];
       }
       // L = E^T Sinv   (Sinv symmetric)
       const double S[9] = {s00, s01, s02, s01, s11, s12, s02, s12, s22};
@@ -937,6 +941,28 @@ k_pack_step(const double* __restrict__ w, const double* __restrict__ g, int32_t 
   double s[1] = {wg};
   grid_reduce_sum<1, kVecThreads>(s, partials, ticket, scal + S_WG);
 }
+// True residual of the LM linear system after the solve, from the SAME products the model-cost step forms:
+// q = H w (k_spmv with the undamped diagonal blocks), so r_true = g - q - Lambda w, Lambda_c = lmdiag_c / (radius scale_c^2).
+// S_TRES = |r_true|^2 over the parameter rows; the caller divides by |g|^2 (S_RR0 of the solve).
+__global__ void __launch_bounds__(kVecThreads)
+k_true_residual(const double* __restrict__ g, const double* __restrict__ q, const double* __restrict__ w,
+                const double* __restrict__ lmdiag, const double* __restrict__ scale, const uint8_t* __restrict__ is_free,
+                int32_t nrows, int64_t ldn, double inv_radius, double* partials, unsigned int* ticket, double* scal) {
+  const int32_t i = blockIdx.x * kVecThreads + threadIdx.x;
+  double rr = 0;
+  if (i < nrows && is_free[i]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double sc = scale[c * ldn + i];
+      const double lam = lmdiag[c * ldn + i] * inv_radius / (sc * sc);
+      const double r = g[c * ldn + i] - q[c * ldn + i] - lam * w[c * ldn + i];
+      rr = fma(r, r, rr);
+    }
+  }
+  double s[1] = {rr};
+  grid_reduce_sum<1, kVecThreads>(s, partials, ticket, scal + S_TRES);
+}
+
 // candidate = x - w (delta = -w);  S_STEP_SQ = |w|^2;  S_XSQ = |candidate|^2 over parameter rows
 __global__ void __launch_bounds__(kVecThreads)
 k_apply_step(const double4* __restrict__ xyt, const double* __restrict__ w, const uint8_t* __restrict__ is_free,

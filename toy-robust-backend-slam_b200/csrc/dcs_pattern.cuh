@@ -155,15 +155,13 @@ __global__ void k_row_ptr(const uint64_t* keys, int32_t nh, int32_t row_lo, int3
   row_ptr[r] = lo;
 }
 
-// ---- jagged-diagonal re-layout per window of kWindow rows ----------------------------------------
-// Rows of a window are ranked by decreasing degree (stable); slot of (row, k-th entry) =
-// round_ptr[window][k] + rank(row).  A warp task = 32 consecutive ranks of one window: its lanes read 32
-// consecutive slots in every round (coalesced) and have near-equal degrees (97% lane efficiency at
-// kWindow = 1024 on the 1M-pose benchmark graph, 86% at 128).
-// pass 1: rank of each row inside its window, max degree per window
+// ---- sliced-ELL re-layout (SELL-32, sorting window kWindow rows) ----------------------------------
+// Rows of a window are ranked by decreasing degree (stable) and stored in rank order.  A warp task = 32 consecutive
+// ranks: its lanes have near-equal degrees (97% lane efficiency at kWindow = 1024 on the 1M-pose benchmark graph,
+// 86% at 128), its k-th half-edges are one 32-slot tile, its tiles are consecutive (see RowLayout).
+// pass 1: rank of each row inside its window
 __global__ void __launch_bounds__(kWindow)
-k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t* rank_of, uint16_t* perm, uint32_t* rank_info,
-           int32_t* win_rounds) {
+k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t* rank_of, uint16_t* perm, uint32_t* rank_info) {
   __shared__ int32_t s_deg[kWindow];
   __shared__ int32_t s_own[kWindow];
   const int32_t r = blockIdx.x * kWindow + threadIdx.x;
@@ -191,37 +189,16 @@ k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t
   perm[(int64_t)blockIdx.x * kWindow + rank] = (uint16_t)threadIdx.x;
   // what a warp task needs to start, in one coalesced word per rank: local row (10 bits) | degree
   rank_info[(int64_t)blockIdx.x * kWindow + rank] = ((uint32_t)d << 10) | (uint32_t)threadIdx.x;
-  if (rank == 0) win_rounds[blockIdx.x] = d + 1;   // rounds + 1 entries in round_ptr
 }
-// pass 2: round_ptr[rp_off[w] + k] = first JDS slot of round k of window w
-__global__ void __launch_bounds__(kWindow)
-k_jds_rounds(const int32_t* row_ptr, int32_t nrows, const int32_t* rp_off, int32_t* round_ptr, int32_t* round32) {
-  __shared__ int32_t s_deg[kWindow];
-  const int32_t r0 = blockIdx.x * kWindow;
-  const int32_t r = r0 + threadIdx.x;
-  s_deg[threadIdx.x] = (r < nrows) ? row_ptr[r + 1] - row_ptr[r] : 0;
-  __syncthreads();
-  const int32_t base = row_ptr[min(r0, nrows)];
-  const int32_t off = rp_off[blockIdx.x];
-  const int32_t nround = rp_off[blockIdx.x + 1] - off;   // max degree + 1
-  // round k starts after sum_rows min(deg, k)
-  for (int32_t k = threadIdx.x; k < nround; k += kWindow) {
-    int32_t s = 0;
-    for (int u = 0; u < kWindow; ++u) s += min(s_deg[u], k);
-    round_ptr[off + k] = base + s;
-    if (k < 32) round32[blockIdx.x * 32 + k] = base + s;   // first 32 round starts at a fixed stride (no rp_off hop)
-  }
-  if ((int)threadIdx.x < 32 && (int)threadIdx.x >= nround) round32[blockIdx.x * 32 + threadIdx.x] = 0;
-}
-// pass 3: sorted CSR position -> JDS slot
-__global__ void k_jds_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, const int32_t* row_ptr,
-                           const uint16_t* rank_of, const int32_t* rp_off, const int32_t* round_ptr, int32_t* slot) {
+// pass 2: sorted CSR position -> SELL slot = (first tile of the row's task + k) * 32 + lane
+__global__ void k_sell_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, const int32_t* row_ptr,
+                            const uint16_t* rank_of, const int32_t* tile0, int32_t* slot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nh) return;
   const int32_t r = (int32_t)(keys[i] >> 32) - row_lo;
   const int32_t k = i - row_ptr[r];
-  const int32_t w = r / kWindow;
-  slot[i] = round_ptr[rp_off[w] + k] + rank_of[r];
+  const int32_t m = row_pos(rank_of, r);               // stored position: task = m / 32, lane = m % 32
+  slot[i] = (tile0[m >> 5] + k) * kSlice + (m & 31);
 }
 
 // ---- odometry-chain entries for the segment preconditioner --------------------------------------------

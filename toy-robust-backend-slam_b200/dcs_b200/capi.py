@@ -39,7 +39,7 @@ class Options(C.Structure):
                 ("pcg_rel_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("pcg_check_every", C.c_int32),
                 ("preconditioner", C.c_int32),
                 ("device", C.c_int32), ("verbose", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("nccl_unique_id", C.c_void_p)]
+                ("nccl_unique_id", C.c_void_p), ("max_solver_time_s", C.c_double)]
 
 
 class Iteration(C.Structure):
@@ -48,7 +48,7 @@ class Iteration(C.Structure):
                 ("gradient_max_norm", C.c_double), ("gradient_norm", C.c_double), ("step_norm", C.c_double),
                 ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double),
                 ("linear_solver_residual", C.c_double), ("iteration_time_s", C.c_double),
-                ("cumulative_time_s", C.c_double)]
+                ("cumulative_time_s", C.c_double), ("linear_solver_true_residual", C.c_double)]
 
 
 class Summary(C.Structure):
@@ -91,7 +91,7 @@ def load_library():
     vp = C.c_void_p
     lib.dcs_evaluate.argtypes = [vp, vp, C.POINTER(C.c_double), vp, vp, vp, vp, vp]
     lib.dcs_linearize.argtypes = [vp, vp, C.POINTER(C.c_double), vp]
-    lib.dcs_linearize_resident.argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
+    lib.dcs_linearize_resident.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     lib.dcs_cost.argtypes = [vp, vp, C.POINTER(C.c_double)]
     lib.dcs_get_pattern.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, vp]
     lib.dcs_get_hessian.argtypes = [vp, vp]
@@ -332,9 +332,9 @@ class Solver:
         self._ck(self.lib.dcs_linearize(self.h, _ptr(x), C.byref(cost), _ptr(g)), "dcs_linearize")
         return cost.value, g
 
-    def linearize_resident(self, repeats=1):
+    def linearize_resident(self, repeats=1, with_solver_setup=False):
         ms = C.c_float()
-        self._ck(self.lib.dcs_linearize_resident(self.h, repeats, C.byref(ms)), "dcs_linearize_resident")
+        self._ck(self.lib.dcs_linearize_resident(self.h, repeats, 1 if with_solver_setup else 0, C.byref(ms)), "dcs_linearize_resident")
         return ms.value
 
     def cost(self, pose_xyt=None):
