@@ -111,6 +111,13 @@ typedef struct dcs_options {
   const void* nccl_unique_id;     /* 128-byte ncclUniqueId shared by all ranks           */
   double max_solver_time_s;       /* 1e6: Solver::Options::max_solver_time_in_seconds (checked between iterations; with
                                    * world > 1 rank 0's clock decides for everybody)      */
+  /* METHOD 2 — switchable constraints (main.cpp:55 SC_ON, :105-150; src/ceres_error.cpp:203-317): every closure / bogus
+   * edge carries a scalar switch s (initial 1), e = s * e_plain with HuberLoss(0.01), plus the prior row
+   * sqrt(lambda) (1 - s) without loss.  Exclusive with dcs_on; single-rank handles only.  The switches are
+   * eliminated edge by edge inside the linear solve (exact Schur complement onto the 3x3 pose blocks) and
+   * recovered after it; dcs_get_switches returns them.                                                        */
+  int32_t switchable_on;          /* METHOD==2                                           */
+  double switch_prior_lambda;     /* 1.0 (main.cpp:110 sc_prior_lambda)                  */
 } dcs_options;
 
 typedef struct dcs_iteration {
@@ -210,6 +217,26 @@ DCS_API int dcs_pcg_solve(dcs_handle* h, const double* lambda, const double* rhs
  * include/graph.h:10-17).  trace may be NULL; trace_cap entries are written at most. */
 DCS_API int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* summary,
               dcs_iteration* trace, int32_t trace_cap);
+
+/* Batched tiny solves — the form the METHOD 3/4 clients need (src/layer_manager.cpp:137-179, :602-654;
+ * src/simple_layer_manager.cpp:173-211, :567-622: a fresh ceres::Problem of odometry + a few candidate loop edges with
+ * OdometryResidue + HuberLoss, 1-2 iterations of ceres::Solve, summary.final_cost read back, thousands of times).
+ * Every item is an independent problem (its own graph, poses copied in; pose_xyt_inout may be NULL when only the
+ * summary is wanted); all items run with the same options.  n_threads host threads (<= 0: 8) each drive one
+ * handle / stream at a time, so the launches of several small solves overlap on the device.  status per item;
+ * the call returns the first non-zero status.  Results are identical to n_items separate dcs_create / dcs_solve
+ * / dcs_destroy sequences (every solve is deterministic on its own stream). */
+typedef struct dcs_batch_item {
+  dcs_graph graph;
+  double* pose_xyt_inout;         /* n_poses x 3 or NULL                                 */
+  dcs_summary summary;            /* out                                                 */
+  int32_t status;                 /* out: DCS_OK or the error of this item               */
+} dcs_batch_item;
+DCS_API int dcs_solve_batch(dcs_batch_item* items, int32_t n_items, const dcs_options* options, int32_t n_threads);
+
+/* METHOD 2: the switch value of every edge after the last dcs_solve (n_edges doubles, residual-block order;
+ * odometry edges carry no switch and read 1.0) — what main.cpp:169-171 hands to writePoseGraph_switches. */
+DCS_API int dcs_get_switches(dcs_handle* h, double* switches);
 
 /* Page-locked host buffers (cudaHostAlloc).  Pose / gradient arrays handed to dcs_linearize, dcs_evaluate and
  * dcs_solve may live anywhere; when they are page-locked the library DMAs straight from / into them instead of

@@ -68,6 +68,11 @@ def test_two_gpu_ranks_match_single_rank():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "MGPU 2 ranks" in p.stdout
+    # once more on the -DDCS_CHECK build: device-side bounds asserts on the halo-indexed gathers
+    lib = os.path.join(ROOT, "toy-robust-backend-slam_b200", "libdcs_b200_check.so")
+    cmd[cmd.index("29517")] = "29521"
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, DCS_B200_LIB=lib))
+    assert p.returncode == 0 and "DCS_CHECK failed" not in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
 @pytest.mark.gpu

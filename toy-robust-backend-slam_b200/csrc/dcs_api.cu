@@ -6,12 +6,14 @@
 // No CPU fallback anywhere: every entry point that computes fails with DCS_ERR_CUDA if the CUDA
 // runtime does.  Nothing here includes, links or loads anything under oracle/.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dcs_b200.h"
@@ -19,13 +21,14 @@
 #include "dcs_kernels.cuh"
 #include "dcs_nccl.h"
 #include "dcs_pattern.cuh"
+#include "dcs_switchable.cuh"
 
 using namespace dcs;
 
 namespace {
 
 thread_local std::string g_err;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};    // dcs_solve_batch drives several handles from several host threads
 
 #define CK(call)                                                                                 \
   do {                                                                                           \
@@ -124,6 +127,11 @@ __global__ void k_fill_halfedges(const uint64_t* __restrict__ keys, const uint32
   r.tmx = tmx[e]; r.tmy = tmy[e]; r.thm = thm[e]; r.word = word; r.word_next = 0u;   // word_next: k_task_walk
   recs[s] = r;
   edge_slot[2 * (int64_t)e + (side_b ? 1 : 0)] = s;
+}
+
+__global__ void k_fill_value(double* p, int64_t n, double v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 // mirror_src[slot]: slot of the partner half-edge whose (owner) block this slot mirrors, or -1
@@ -252,6 +260,13 @@ struct dcs_handle {
   int pcg_graph_iters = 0;
   const double* pcg_graph_D = nullptr;
   bool have_lin = false;
+  // METHOD 2 (switchable constraints, dcs_switchable.cuh): one switch per loop edge, eliminated inside the linear solve
+  bool sc = false;
+  double sc_lambda = 1.0;
+  DevBuf<double> sw, sw_cand, sw_scale;    // [E] switch values (accepted / candidate), Jacobi scale of the switch columns
+  DevBuf<double2> sw_slot;                 // [ldh] (s, scale) of the slot's edge: what k_linearize_sc streams
+  DevBuf<int32_t> edge_slot;               // [2 E] slots of an edge's two half-edges (-1: none)
+  DevBuf<double> Hdiag_lm, grad_full;      // unreduced pose diagonal blocks / gradient (Jacobi scale, LM diagonal, model cost)
   double eval_ms = 0, pcg_ms = 0;
   int64_t pcg_iters_total = 0;
 
@@ -525,7 +540,30 @@ int download_poses(dcs_handle* h, const double4* xyt, double* pose_xyt) {
 }
 
 // K1+K2 at the given packed poses; results in Hoff / Hdiag / grad, scalars S_COST, S_GSQ, S_GMAX
+int sc_args(const dcs_handle* h, double inv_radius, int reduce, ScArgs* A) {
+  A->lambda = h->sc_lambda; A->inv_radius = inv_radius; A->dmin = h->opt.min_lm_diagonal; A->dmax = h->opt.max_lm_diagonal; A->reduce = reduce;
+  return DCS_OK;
+}
+// METHOD 2: the row-owner pass at (xyt, sw).  reduce = 0: the pose blocks of J^T J and J^T r as they are (+ cost and
+// the gradient norms over poses and switches); reduce = 1: the switches eliminated for the step at this radius.
+int linearize_sc(dcs_handle* h, const double4* xyt, double inv_radius, int reduce) {
+  ScArgs A;
+  sc_args(h, inv_radius, reduce, &A);
+  if (h->E > 0) LAUNCH(k_sc_to_slots, cdiv(h->E, 256), 256, h->stream, h->edge_slot.p, h->e_dcs.p, h->E, h->sw.p, h->sw_scale.p, h->sw_slot.p);
+  LAUNCH(k_linearize_sc, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->sw_slot.p, h->P, A, h->n_loc, h->Hup.p,
+         h->Hdiag.p, h->grad.p, h->task_part.p);
+  if (!reduce) {
+    k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
+    ++g_launches;
+  }
+  h->have_lin = true;
+  h->mirrored = false;
+  h->mirrored32 = false;
+  return DCS_OK;
+}
+
 int linearize(dcs_handle* h, const double4* xyt) {
+  if (h->sc) return linearize_sc(h, xyt, 0.0, 0);
   LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->P, h->n_loc, h->Hup.p, h->Hdiag.p,
          h->grad.p, h->task_part.p);
   k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
@@ -558,7 +596,15 @@ int ensure_mirror(dcs_handle* h, bool single = false) {
   return DCS_OK;
 }
 
-int cost_only(dcs_handle* h, const double4* xyt, int slot) {
+int cost_only(dcs_handle* h, const double4* xyt, int slot, const double* sw = nullptr) {
+  if (h->sc) {     // METHOD 2: edge-order pass at (xyt, sw); results in S_SC_COST (cost) and S_SC_COST + 1 (sum s^2)
+    ScArgs A;
+    sc_args(h, 0.0, 0, &A);
+    LAUNCH(k_sc_edges<kScCost>, std::max(1, cdiv(h->E, kEdgeThreads)), kEdgeThreads, h->stream, xyt, h->g2l.p, h->edgelist(), h->P, A, 0,
+           sw ? sw : h->sw.p, (double*)nullptr, (const double*)nullptr, h->ldn, (double*)nullptr, h->partials.p, h->tickets.p + 4,
+           h->scal.p + S_SC_COST);
+    return DCS_OK;
+  }
   LAUNCH(k_cost_rows, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->P, h->n_loc, h->task_part.p);
   k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + slot, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
   ++g_launches;
@@ -682,6 +728,8 @@ void dcs_options_default(dcs_options* o) {
   o->world = 1;
   o->nccl_unique_id = nullptr;
   o->max_solver_time_s = 1e6;
+  o->switchable_on = 0;
+  o->switch_prior_lambda = 1.0;
 }
 
 void* dcs_host_alloc(uint64_t bytes) {
@@ -693,7 +741,7 @@ void dcs_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 const char* dcs_version(void) { return "dcs_b200 0.1 (sm_100a)"; }
 const char* dcs_last_error(void) { return g_err.c_str(); }
-int64_t dcs_launch_count(int reset) { const int64_t v = g_launches; if (reset) g_launches = 0; return v; }
+int64_t dcs_launch_count(int reset) { const int64_t v = g_launches.load(); if (reset) g_launches = 0; return v; }
 
 int dcs_device_count(void) {
   int n = 0;
@@ -745,6 +793,9 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   if (g->n_edges > 0 && (!g->edge_a || !g->edge_b || !g->meas_xyt || !g->kind)) { g_err = "dcs_create: null edge array"; return DCS_ERR_ARG; }
   if ((uint32_t)g->n_poses > kIdxMask) { g_err = "dcs_create: too many poses"; return DCS_ERR_ARG; }
   if (g->fixed_pose < -1 || g->fixed_pose >= g->n_poses) { g_err = "dcs_create: fixed_pose must be -1 (none) or a pose index"; return DCS_ERR_ARG; }
+  if (o->switchable_on && o->dcs_on) { g_err = "dcs_create: dcs_on and switchable_on are exclusive (METHOD 1 vs METHOD 2)"; return DCS_ERR_ARG; }
+  if (o->switchable_on && o->world > 1) { g_err = "dcs_create: switchable constraints (METHOD 2) run on single-rank handles only"; return DCS_ERR_ARG; }
+  if (o->switchable_on && !(o->switch_prior_lambda > 0.0)) { g_err = "dcs_create: switch_prior_lambda must be positive"; return DCS_ERR_ARG; }
   if (o->world > kMaxWorld) { g_err = "dcs_create: world sizes above " + std::to_string(kMaxWorld) + " (one NVSwitch node) are not supported"; return DCS_ERR_ARG; }
   for (int32_t k = 0; k < g->n_edges; ++k) {
     const int32_t a = g->edge_a[k], b = g->edge_b[k];
@@ -777,6 +828,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   h->P.phi = o->phi; h->P.hub_a = o->huber_delta; h->P.hub_b = o->huber_delta * o->huber_delta;
   h->N = g->n_poses; h->E = g->n_edges; h->fixed = g->fixed_pose;
   h->rank = o->rank; h->world = std::max(1, o->world);
+  h->sc = o->switchable_on != 0; h->sc_lambda = o->switch_prior_lambda;
   if (h->rank < 0 || h->rank >= h->world) { g_err = "dcs_create: bad rank"; return DCS_ERR_ARG; }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
@@ -818,7 +870,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const size_t EE = (size_t)std::max(E, 1);
   CK(h->e_tmx.alloc(EE)); CK(h->e_tmy.alloc(EE)); CK(h->e_thm.alloc(EE));
   CK(h->e_dcs.alloc(EE));
-  if (E > 0) LAUNCH(k_edge_prep, cdiv(E, 256), 256, st, d_meas.p, d_kind.p, E, o->dcs_on, h->e_tmx.p, h->e_tmy.p, h->e_thm.p,
+  if (E > 0) LAUNCH(k_edge_prep, cdiv(E, 256), 256, st, d_meas.p, d_kind.p, E, o->dcs_on || o->switchable_on, h->e_tmx.p, h->e_tmy.p, h->e_thm.p,
                     h->e_dcs.p);
 
   lap("upload + edge prep");
@@ -903,6 +955,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     if (nh > 0) LAUNCH(k_block_src, cdiv(nh, 256), 256, st, h->cols.p, h->slot.p, mirror_src.p, cidx.p, nh, h->block_src.p);
     CK(cudaStreamSynchronize(st));     // n_own on the host; the scratch arrays are freed here
     h->ldu = ((int64_t)std::max(n_own, 1) + 31) / 32 * 32;
+    if (h->sc) { std::swap(h->edge_slot.p, edge_slot.p); std::swap(h->edge_slot.n, edge_slot.n); }
   }
 
   lap("sell layout + fill");
@@ -925,7 +978,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->scale.alloc_zero(3 * LN, st)); CK(h->lmdiag.alloc_zero(3 * LN, st)); CK(h->Adiag.alloc_zero(6 * LN, st)); CK(h->Minv.alloc_zero(6 * LN, st));
   CK(h->w.alloc_zero(3 * LN, st)); CK(h->r.alloc_zero(3 * LN, st)); CK(h->q.alloc_zero(3 * LN, st)); CK(h->z.alloc_zero(3 * LN, st));
   CK(h->lambda_tmp.alloc_zero(3 * LN, st)); CK(h->rhs_tmp.alloc_zero(3 * LN, st));
-  const size_t max_grid = (size_t)std::max<int64_t>({(int64_t)h->nblk, (int64_t)h->vec_grid(), 148 * 8});
+  const size_t max_grid = (size_t)std::max<int64_t>({(int64_t)h->nblk, (int64_t)h->vec_grid(), 148 * 8, 2 * (int64_t)cdiv(E, kEdgeThreads)});
   CK(h->partials.alloc_zero(4 * max_grid, st));
   CK(h->scal.alloc_zero(S_COUNT, st));
   CK(h->tickets.alloc_zero(8, st));
@@ -940,6 +993,14 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->rank_scal.alloc_zero((size_t)h->world * 4, st));
   CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
   CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
+  if (h->sc) {
+    CK(h->sw.alloc(EE)); CK(h->sw_cand.alloc(EE)); CK(h->sw_scale.alloc(EE));
+    CK(h->sw_slot.alloc_zero(HH, st));
+    CK(h->Hdiag_lm.alloc_zero(6 * LN, st)); CK(h->grad_full.alloc_zero(3 * LN, st));
+    LAUNCH(k_fill_value, cdiv((int64_t)EE, 256), 256, st, h->sw.p, (int64_t)EE, 1.0);
+    LAUNCH(k_fill_value, cdiv((int64_t)EE, 256), 256, st, h->sw_cand.p, (int64_t)EE, 1.0);
+    LAUNCH(k_fill_value, cdiv((int64_t)EE, 256), 256, st, h->sw_scale.p, (int64_t)EE, 1.0);
+  }
   lap("state alloc");
   CKS(setup_halo_push(h));
   CKS(upload_poses(h, g->pose_xyt, h->xyt.p));
@@ -1169,6 +1230,10 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
   auto timed_linearize = [&](const double4* x) -> int {
     CK(cudaEventRecord(h->ev0, st));
     CKS(linearize(h, x));
+    if (h->sc) {   // the reduced pass of every LM step overwrites Hdiag / grad: keep the pose blocks' diagonal and J_p^T r
+      CK(cudaMemcpyAsync(h->Hdiag_lm.p, h->Hdiag.p, 6 * (size_t)h->ldn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(h->grad_full.p, h->grad.p, 3 * (size_t)h->ldn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
     CK(cudaEventRecord(h->ev1, st));
     CKS(read_scalars(h));
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1179,16 +1244,31 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
   CKS(upload_poses(h, pose_xyt_inout, h->xyt.p));
   LAUNCH(k_xnorm, h->vec_grid(), kVecThreads, st, h->xyt.p, h->is_free.p, 0, h->nrows, h->partials.p, h->tickets.p + 5, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_XSQ, 1));
+  const double* Hdiag_lm = h->sc ? h->Hdiag_lm.p : h->Hdiag.p;     // pose diagonal blocks of J^T J (METHOD 2: before the elimination)
+  const double* grad_full = h->sc ? h->grad_full.p : h->grad.p;
+  if (h->sc) {     // every solve starts with all switches at 1 (main.cpp:117,139) and unit column scales
+    const int64_t EE = std::max(h->E, 1);
+    LAUNCH(k_fill_value, cdiv(EE, 256), 256, st, h->sw.p, EE, 1.0);
+    LAUNCH(k_fill_value, cdiv(EE, 256), 256, st, h->sw_scale.p, EE, 1.0);
+    CKS(cost_only(h, h->xyt.p, S_CAND_COST));                        // S_SC_COST + 1 = sum s^2 for |x|
+  }
   CKS(timed_linearize(h->xyt.p));
   double x_cost = h->h_scal[S_COST];
-  double x_norm = std::sqrt(h->h_scal[S_XSQ]);
+  double x_norm = std::sqrt(h->h_scal[S_XSQ] + (h->sc ? h->h_scal[S_SC_COST + 1] : 0.0));
   if (!std::isfinite(x_cost)) {
     sum->termination_type = DCS_FAILURE;
     std::snprintf(sum->message, sizeof(sum->message), "Initial cost is not finite.");
     g_err = sum->message;
     return DCS_ERR_NUMERIC;
   }
-  LAUNCH(k_jacobi_scale, h->vec_grid(), 256, st, h->Hdiag.p, h->nrows, h->ldn, h->scale.p, o.jacobi_scaling);
+  LAUNCH(k_jacobi_scale, h->vec_grid(), 256, st, Hdiag_lm, h->nrows, h->ldn, h->scale.p, o.jacobi_scaling);
+  if (h->sc) {
+    ScArgs A;
+    sc_args(h, 0.0, 0, &A);
+    LAUNCH(k_sc_edges<kScScale>, std::max(1, cdiv(h->E, kEdgeThreads)), kEdgeThreads, st, h->xyt.p, h->g2l.p, h->edgelist(), h->P, A,
+           o.jacobi_scaling, h->sw.p, h->sw_scale.p, (const double*)nullptr, h->ldn, (double*)nullptr, h->partials.p, h->tickets.p + 4,
+           h->scal.p + S_SC);
+  }
 
   int n_logged = 0;
   double min_logged_cost = std::numeric_limits<double>::max();
@@ -1246,16 +1326,24 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     it.iteration = prev.iteration + 1;
 
     if (!reuse_diagonal)
-      LAUNCH(k_lm_diagonal, h->vec_grid(), 256, st, h->Hdiag.p, h->scale.p, h->nrows, h->ldn, o.min_lm_diagonal, o.max_lm_diagonal, h->lmdiag.p);
+      LAUNCH(k_lm_diagonal, h->vec_grid(), 256, st, Hdiag_lm, h->scale.p, h->nrows, h->ldn, o.min_lm_diagonal, o.max_lm_diagonal, h->lmdiag.p);
     reuse_diagonal = true;
     int pcg_it = 0;
     double pcg_rel = 0;
+    if (h->sc) {   // the switches' Schur complement depends on the radius: re-assemble the reduced system for this step
+      CK(cudaEventRecord(h->ev0, st));
+      CKS(linearize_sc(h, h->xyt.p, 1.0 / radius, 1));
+      CK(cudaEventRecord(h->ev1, st));
+      CK(cudaEventSynchronize(h->ev1));
+      CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      h->eval_ms += ms;
+    }
     CKS(pcg_solve(h, 1.0 / radius, nullptr, h->grad.p, &pcg_it, &pcg_rel));
     it.linear_solver_iterations = pcg_it;
     it.linear_solver_residual = pcg_rel;
 
     // model_cost_change = w.g - w.H.w / 2
-    LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, h->grad.p, 0, h->nrows, h->ldn, h->p4.p, h->partials.p,
+    LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, grad_full, 0, h->nrows, h->ldn, h->p4.p, h->partials.p,
            h->tickets.p + 4, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
     CKS(halo_exchange(h, h->p4.p));
@@ -1273,16 +1361,32 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
            h->partials.p, h->tickets.p + 5, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_STEP_SQ, 2));
     CKS(halo_exchange(h, h->cand_xyt.p));
+    if (h->sc) {   // switch steps from the pose step (back-substitution of the elimination) + their model-cost terms
+      ScArgs A;
+      sc_args(h, 1.0 / radius, 1, &A);
+      LAUNCH(k_sc_edges<kScStep>, std::max(1, cdiv(h->E, kEdgeThreads)), kEdgeThreads, st, h->xyt.p, h->g2l.p, h->edgelist(), h->P, A,
+             o.jacobi_scaling, h->sw.p, h->sw_scale.p, h->w.p, h->ldn, h->sw_cand.p, h->partials.p, h->tickets.p + 4, h->scal.p + S_SC);
+    }
     CK(cudaEventRecord(h->ev0, st));
-    CKS(cost_only(h, h->cand_xyt.p, S_CAND_COST));
+    CKS(cost_only(h, h->cand_xyt.p, S_CAND_COST, h->sw_cand.p));
     CK(cudaEventRecord(h->ev1, st));
     CKS(read_scalars(h));
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->eval_ms += ms;
-    const double wg = h->h_scal[S_WG], whw = h->h_scal[S_WHW];
+    double wg = h->h_scal[S_WG], whw = h->h_scal[S_WHW];
+    double step_sq = h->h_scal[S_STEP_SQ], cand_xsq = h->h_scal[S_XSQ];
+    if (h->sc) {   // model cost change over poses AND switches: w.g + ws.g_s - (w.H.w + ws.H_ss.ws + 2 ws.H_sx.w) / 2,
+                   // with w.H.w = w.H_reduced.w + sum (H_sx.w)^2 / den
+      const double* q = h->h_scal + S_SC;
+      wg += q[0];
+      whw += q[2] + q[1];
+      step_sq += q[3];
+      cand_xsq += q[4];
+      h->h_scal[S_CAND_COST] = h->h_scal[S_SC_COST];
+    }
     it.linear_solver_true_residual = h->h_scal[S_RR0] > 0.0 ? std::sqrt(h->h_scal[S_TRES] / h->h_scal[S_RR0]) : 0.0;
     const double model_cost_change = wg - 0.5 * whw;
-    const bool finite_step = std::isfinite(wg) && std::isfinite(whw) && std::isfinite(h->h_scal[S_STEP_SQ]);
+    const bool finite_step = std::isfinite(wg) && std::isfinite(whw) && std::isfinite(step_sq);
     it.step_is_valid = finite_step && model_cost_change > 0.0;
     if (!it.step_is_valid) {
       if (++invalid >= o.max_num_consecutive_invalid_steps) {
@@ -1298,7 +1402,7 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     invalid = 0;
     double cand = h->h_scal[S_CAND_COST];
     if (!std::isfinite(cand)) cand = std::numeric_limits<double>::max();
-    it.step_norm = std::sqrt(h->h_scal[S_STEP_SQ]);
+    it.step_norm = std::sqrt(step_sq);
     it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
     if (it.step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) {
       term = DCS_CONVERGENCE; msg = "Parameter tolerance reached.";
@@ -1317,7 +1421,8 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
                                                                           : (x_cost - cand) / model_cost_change;
     if (it.relative_decrease > o.min_relative_decrease) {
       std::swap(h->xyt.p, h->cand_xyt.p);
-      x_norm = std::sqrt(h->h_scal[S_XSQ]);
+      if (h->sc) std::swap(h->sw.p, h->sw_cand.p);
+      x_norm = std::sqrt(cand_xsq);
       CKS(timed_linearize(h->xyt.p));
       x_cost = h->h_scal[S_COST];
       it.step_is_successful = 1;
@@ -1351,6 +1456,54 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
   sum->linear_solver_time_s = h->pcg_ms * 1e-3;
   std::snprintf(sum->message, sizeof(sum->message), "%s", msg);
   CK(cudaGetLastError());
+  return DCS_OK;
+}
+
+// N3: many small independent solves at once.  One handle + one stream per problem, n_threads host threads pulling
+// problems from a shared counter: the kernels of several tiny solves (each far too small to fill 148 SMs, each
+// latency-bound on its own host round trips) overlap on the device.
+int dcs_solve_batch(dcs_batch_item* items, int32_t n_items, const dcs_options* options, int32_t n_threads) {
+  if (!items || n_items < 0 || !options) { g_err = "dcs_solve_batch: bad argument"; return DCS_ERR_ARG; }
+  if (options->world > 1) { g_err = "dcs_solve_batch: single-rank only"; return DCS_ERR_ARG; }
+  if (n_items == 0) return DCS_OK;
+  const int nt = std::max(1, std::min<int>({n_threads > 0 ? n_threads : 8, n_items, 64}));
+  std::atomic<int32_t> next{0};
+  std::vector<std::string> errs((size_t)n_items);
+  auto worker = [&]() {
+    for (;;) {
+      const int32_t i = next.fetch_add(1);
+      if (i >= n_items) return;
+      dcs_batch_item& it = items[i];
+      std::memset(&it.summary, 0, sizeof(it.summary));
+      dcs_handle* h = nullptr;
+      int rc = dcs_create(&it.graph, options, &h);
+      if (rc == DCS_OK) {
+        std::vector<double> tmp;
+        double* x = it.pose_xyt_inout;
+        if (!x) { tmp.assign(it.graph.pose_xyt, it.graph.pose_xyt + 3 * (size_t)it.graph.n_poses); x = tmp.data(); }
+        rc = dcs_solve(h, x, &it.summary, nullptr, 0);
+      }
+      if (rc != DCS_OK) errs[(size_t)i] = g_err;      // g_err is thread-local: carry the text to the caller's thread
+      if (h) dcs_destroy(h);
+      it.status = rc;
+    }
+  };
+  if (nt == 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+  }
+  for (int32_t i = 0; i < n_items; ++i)
+    if (items[i].status != DCS_OK) { g_err = "dcs_solve_batch: item " + std::to_string(i) + ": " + errs[(size_t)i]; return items[i].status; }
+  return DCS_OK;
+}
+
+int dcs_get_switches(dcs_handle* h, double* switches) {
+  if (!h || !switches) return DCS_ERR_ARG;
+  if (!h->sc) { g_err = "dcs_get_switches: the handle was not created with switchable_on"; return DCS_ERR_ARG; }
+  CK(cudaSetDevice(h->dev));
+  if (h->E > 0) CK(cudaMemcpy(switches, h->sw.p, (size_t)h->E * sizeof(double), cudaMemcpyDeviceToHost));
   return DCS_OK;
 }
 

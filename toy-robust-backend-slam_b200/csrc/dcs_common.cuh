@@ -238,7 +238,9 @@ __device__ __forceinline__ EdgeFrame edge_frame(double ox, double oy, double oth
 
 // cost of one edge and the intermediates the normal-equation terms reuse
 struct EdgeCore { double q00, q01, epx, epy, ex, ey, t, psi2, inv_den, e2, rho1, cost; };
-__device__ __forceinline__ EdgeCore edge_core(const EdgeFrame& F, double tmx, double tmy, double thm, bool dcs, const Params& P) {
+// kSwitch (METHOD 2, dcs_switchable.cuh): the error is scaled by the edge's switch value sw instead of the DCS weight
+template <bool kSwitch>
+__device__ __forceinline__ EdgeCore edge_core_t(const EdgeFrame& F, double tmx, double tmy, double thm, bool dcs, double sw, const Params& P) {
   EdgeCore C;
   sincos_cw(F.tha + thm, C.q01, C.q00);     // Q = Rm^T Ra^T = R(-(tha + thm)); one sincos per half-edge instead of
                                             // streaming cos/sin of the measurement and gathering cos/sin of the pose
@@ -250,16 +252,24 @@ __device__ __forceinline__ EdgeCore edge_core(const EdgeFrame& F, double tmx, do
   C.e2 = fma(C.t, C.t, res);
   // DCS (psi_org < 1 <=> res > phi) and Huber, branch-free: nearly every warp has a lane on either side of both
   // thresholds, so the reciprocal and the reciprocal square root are always computed and selected afterwards
-  const bool active = dcs && res > P.phi;
-  const double inv = fast_rcp(P.phi + res);
-  C.inv_den = active ? inv : 0.0;
-  C.psi2 = active ? 2.0 * P.phi * inv : 1.0;
+  if (kSwitch) {
+    C.inv_den = 0.0;
+    C.psi2 = sw * sw;
+  } else {
+    const bool active = dcs && res > P.phi;
+    const double inv = fast_rcp(P.phi + res);
+    C.inv_den = active ? inv : 0.0;
+    C.psi2 = active ? 2.0 * P.phi * inv : 1.0;
+  }
   const double s = C.psi2 * C.e2;
   const bool lin = s > P.hub_b;
   const double rs = fast_rsqrt(lin ? s : 1.0);
   C.rho1 = lin ? P.hub_a * rs : 1.0;          // >= DBL_MIN for every finite s
   C.cost = lin ? fma(P.hub_a, s * rs, -0.5 * P.hub_b) : 0.5 * s;
   return C;
+}
+__device__ __forceinline__ EdgeCore edge_core(const EdgeFrame& F, double tmx, double tmy, double thm, bool dcs, const Params& P) {
+  return edge_core_t<false>(F, tmx, tmy, thm, dcs, 1.0, P);
 }
 
 __device__ __forceinline__ void edge_terms(const EdgeFrame& F, const EdgeCore& C, EdgeTerms& T) {

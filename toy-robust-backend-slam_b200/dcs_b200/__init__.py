@@ -8,7 +8,7 @@ library's CUDA error when no B200 is usable: there is no CPU fallback.
 """
 from .capi import (DcsError, Graph, Options, Solver, Summary, device_count, launch_count, lib_path,
                    host_lib_path, nccl_unique_id, partition, pinned_empty, version, load_library, load_host_library,
-                   DECLARED_SYMBOLS)
+                   DECLARED_SYMBOLS, solve_batch)
 
 __all__ = ["DcsError", "Graph", "Options", "Solver", "Summary", "device_count", "launch_count", "lib_path",
-           "host_lib_path", "nccl_unique_id", "partition", "pinned_empty", "version", "load_library", "load_host_library", "DECLARED_SYMBOLS"]
+           "host_lib_path", "nccl_unique_id", "partition", "pinned_empty", "version", "load_library", "load_host_library", "DECLARED_SYMBOLS", "solve_batch"]

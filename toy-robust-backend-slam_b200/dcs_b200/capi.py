@@ -39,7 +39,8 @@ class Options(C.Structure):
                 ("pcg_rel_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("pcg_check_every", C.c_int32),
                 ("preconditioner", C.c_int32),
                 ("device", C.c_int32), ("verbose", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("nccl_unique_id", C.c_void_p), ("max_solver_time_s", C.c_double)]
+                ("nccl_unique_id", C.c_void_p), ("max_solver_time_s", C.c_double),
+                ("switchable_on", C.c_int32), ("switch_prior_lambda", C.c_double)]
 
 
 class Iteration(C.Structure):
@@ -58,10 +59,14 @@ class Summary(C.Structure):
                 ("eval_time_s", C.c_double), ("linear_solver_time_s", C.c_double), ("message", C.c_char * 128)]
 
 
+class BatchItem(C.Structure):
+    _fields_ = [("graph", _Graph), ("pose_xyt_inout", C.c_void_p), ("summary", Summary), ("status", C.c_int32)]
+
+
 # every symbol include/dcs_b200.h declares (tests check the .so exports all of them)
 DECLARED_SYMBOLS = ["dcs_options_default", "dcs_version", "dcs_device_count", "dcs_partition", "dcs_nccl_unique_id", "dcs_create",
                     "dcs_destroy", "dcs_evaluate", "dcs_linearize", "dcs_linearize_resident", "dcs_cost",
-                    "dcs_get_pattern", "dcs_get_hessian", "dcs_pcg_solve", "dcs_solve", "dcs_host_alloc", "dcs_host_free",
+                    "dcs_get_pattern", "dcs_get_hessian", "dcs_pcg_solve", "dcs_solve", "dcs_solve_batch", "dcs_get_switches", "dcs_host_alloc", "dcs_host_free",
                     "dcs_last_error",
                     "dcs_launch_count"]
 
@@ -97,6 +102,8 @@ def load_library():
     lib.dcs_get_hessian.argtypes = [vp, vp]
     lib.dcs_pcg_solve.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     lib.dcs_solve.argtypes = [vp, vp, C.POINTER(Summary), C.POINTER(Iteration), C.c_int32]
+    lib.dcs_get_switches.argtypes = [vp, vp]
+    lib.dcs_solve_batch.argtypes = [C.POINTER(BatchItem), C.c_int32, C.POINTER(Options), C.c_int32]
     lib.dcs_nccl_unique_id.argtypes = [vp]
     lib.dcs_host_alloc.restype = C.c_void_p
     lib.dcs_host_alloc.argtypes = [C.c_uint64]
@@ -364,6 +371,12 @@ class Solver:
         self._ck(self.lib.dcs_pcg_solve(self.h, _ptr(lam), _ptr(rhs), _ptr(w), C.byref(it), C.byref(rel)), "dcs_pcg_solve")
         return w, it.value, rel.value
 
+    def switches(self):
+        """METHOD 2: switch value per edge after the last solve (1.0 on odometry edges)."""
+        sw = np.empty(self.graph.n_edges)
+        self._ck(self.lib.dcs_get_switches(self.h, _ptr(sw)), "dcs_get_switches")
+        return sw
+
     def solve(self, pose_xyt=None):
         x = np.array(self.graph.pose_xyt if pose_xyt is None else pose_xyt, dtype=np.float64, order="C")
         s = Summary()
@@ -371,3 +384,29 @@ class Solver:
         trace = (Iteration * cap)()
         self._ck(self.lib.dcs_solve(self.h, _ptr(x), C.byref(s), trace, cap), "dcs_solve")
         return x, s, [trace[i] for i in range(min(cap, s.num_iterations))]
+
+
+def solve_batch(graphs, dcs_on=False, n_threads=8, return_poses=False, **opts):
+    """dcs_solve_batch over a list of Graphs (N3: many tiny independent solves).  Returns (summaries, poses or None)."""
+    lib = load_library()
+    o = Options()
+    lib.dcs_options_default(C.byref(o))
+    o.dcs_on = 1 if dcs_on else 0
+    for k, v in opts.items():
+        setattr(o, k, v)
+    n = len(graphs)
+    items = (BatchItem * max(n, 1))()
+    poses = [np.array(g.pose_xyt, dtype=np.float64, order="C") for g in graphs] if return_poses else None
+    for i, g in enumerate(graphs):
+        items[i].graph = _Graph(g.n_poses, g.n_edges, _ptr(g.pose_xyt), _ptr(g.edge_a), _ptr(g.edge_b), _ptr(g.meas_xyt),
+                                _ptr(g.kind), g.fixed_pose)
+        items[i].pose_xyt_inout = poses[i].ctypes.data if return_poses else None
+    rc = lib.dcs_solve_batch(items, n, C.byref(o), n_threads)
+    if rc:
+        raise DcsError(rc, "dcs_solve_batch", lib.dcs_last_error().decode())
+    sums = []
+    for i in range(n):
+        s = Summary()
+        C.memmove(C.byref(s), C.byref(items[i].summary), C.sizeof(Summary))
+        sums.append(s)
+    return sums, poses

@@ -1,4 +1,4 @@
-// main.cpp — drop-in for the reference's DCS-ceres/main.cpp, METHOD 0 (baseline) and 1 (DCS).
+// main.cpp — drop-in for the reference's DCS-ceres/main.cpp, METHOD 0 (baseline), 1 (DCS) and 2 (switchable constraints).
 //
 //   ./main DATASET_NAME_WITHOUT_DOTG2O NUM_OUTLIER_LOOPS METHOD
 //
@@ -9,8 +9,9 @@
 // dcs_create -> dcs_solve -> dcs_destroy (include/dcs_b200.h).  There is no CPU fallback:
 // without a usable B200 the program reports the CUDA error and exits non-zero.
 //
-// METHOD 2/3/4 (switchable constraints, layer managers) are outside this path; they are refused
-// with a message instead of silently running something else.
+// METHOD 2 adds one switch + prior per loop edge (main.cpp:105-150) and writes save/switches.txt (main.cpp:169-171).
+// METHOD 3/4 (layer managers) are outside this path; they are refused with a message instead of silently
+// running something else.
 //
 // Extra knobs, all through the environment so the CLI stays identical:
 //   DCS_SEED         seed for the outlier injection (reference: time(0), main.cpp:43)
@@ -44,7 +45,7 @@ static const char* termination_name(int t) {
 int main(int argc, char* argv[]) {
   if (argc < 4) {
     cout << "Usage: " << argv[0] << " DATASET NUM_OUTLIER_LOOPS METHOD\n";
-    cout << "METHOD: 0=baseline, 1=DCS (2=Switchable, 3=Layer, 4=Simple Layer MCTS: not on this path)\n";
+    cout << "METHOD: 0=baseline, 1=DCS, 2=Switchable (3=Layer, 4=Simple Layer MCTS: not on this path)\n";
     cout << "Example: " << argv[0] << " INTEL 50 1\n";
     return -1;
   }
@@ -63,8 +64,8 @@ int main(int argc, char* argv[]) {
   g2o_manager.add_random_C(num_bogus_loops);
 
   const int METHOD = atoi(argv[3]);
-  if (METHOD != 0 && METHOD != 1) {
-    std::cerr << "METHOD " << METHOD << " is outside the B200 hot path (only 0=baseline, 1=DCS)." << endl;
+  if (METHOD != 0 && METHOD != 1 && METHOD != 2) {
+    std::cerr << "METHOD " << METHOD << " is outside the B200 hot path (only 0=baseline, 1=DCS, 2=Switchable)." << endl;
     return 2;
   }
 
@@ -93,6 +94,8 @@ int main(int argc, char* argv[]) {
   dcs_options options;
   dcs_options_default(&options);
   options.dcs_on = (METHOD == 1);
+  options.switchable_on = (METHOD == 2);     // SC_ON (main.cpp:55)
+  options.switch_prior_lambda = 1.0;         // sc_prior_lambda (main.cpp:110)
   options.verbose = 1;  // minimizer_progress_to_stdout
   options.device = atoi(env_or("DCS_DEVICE", "0").c_str());
   if (std::getenv("DCS_PCG_TOL")) options.pcg_rel_tol = atof(std::getenv("DCS_PCG_TOL"));
@@ -118,7 +121,8 @@ int main(int argc, char* argv[]) {
   cout << "\nSolver Summary (B200 DCS-LM, block-Jacobi PCG)\n\n";
   cout << "Parameter blocks   " << graph.n_poses << " (1 constant)\n";
   cout << "Residual blocks    " << graph.n_edges << "\n";
-  cout << "Robust loss        HuberLoss(0.01)" << (options.dcs_on ? " + DCS(phi=0.5) on loop edges" : "") << "\n\n";
+  cout << "Robust loss        HuberLoss(0.01)" << (options.dcs_on ? " + DCS(phi=0.5) on loop edges" : "")
+       << (options.switchable_on ? " + one switch and prior (lambda=1) per loop edge" : "") << "\n\n";
   std::printf("Cost:\nInitial        %.6e\nFinal          %.6e\nChange         %.6e\n\n", summary.initial_cost,
               summary.final_cost, summary.initial_cost - summary.final_cost);
   std::printf("Minimizer iterations   %d\nSuccessful steps       %d\nUnsuccessful steps     %d\n", summary.num_iterations,
@@ -130,6 +134,19 @@ int main(int argc, char* argv[]) {
 
   g2o_manager.writePoseGraph_nodes(SAVE_PATH + "/opt_nodes.txt");
   g2o_manager.writePoseGraph_edges(SAVE_PATH + "/opt_edges.txt");
+  if (METHOD == 2) {   // main.cpp:169-171: priors (all 1.0) and optimised switches, closure edges first, then bogus
+    std::vector<double> all((size_t)graph.n_edges, 1.0);
+    rc = dcs_get_switches(handle, all.data());
+    if (rc != DCS_OK) {
+      std::cerr << "dcs_get_switches failed (" << rc << "): " << dcs_last_error() << endl;
+      dcs_destroy(handle);
+      return 3;
+    }
+    const size_t n_odo = g2o_manager.nEdgesOdometry.size();
+    const std::vector<double> optimized(all.begin() + (long)n_odo, all.end());
+    const std::vector<double> priors(optimized.size(), 1.0);
+    g2o_manager.writePoseGraph_switches(SAVE_PATH + "/switches.txt", priors, optimized);
+  }
   dcs_destroy(handle);
   return 0;
 }
