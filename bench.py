@@ -36,6 +36,11 @@ LOOPS_PER_GPU = 2_700_001           # + 999 999 odometry + 300 000 outliers = 4 
 OUTLIERS_PER_GPU = 300_000
 CPU_SAMPLE_POSES = 250_000          # bounded sample of the same generator for the CPU arm
 PARITY_LM_ITERS = 3                 # LM iterations compared N-rank vs 1-rank at weak-scaling bench size
+# Full 50-iteration solves (strong leg): the non-converged LM trajectory at 1 M poses amplifies the 1e-12 residual of
+# its linear solves - the SAME single-GPU solve repeated with pcg_rel_tol 1e-13, or with the other preconditioner, stays
+# within 1e-9 of the default for 16 iterations and has drifted to 2e-4 by iteration 30 (profiles/r02_lm_sensitivity.json).
+# N-rank vs 1-rank is therefore gated on the leading iterations; the rest is reported.
+PARITY_FULL_ITERS = 10
 
 
 def peaks():
@@ -173,13 +178,17 @@ def trace_summary(summ, trace, dt):
 
 
 def compare_traces(tn, t1, k):
-    """accept/reject sequence and costs of the first k logged iterations."""
+    """accept/reject sequence and costs of the first k logged iterations; also how many leading iterations agree to 1e-9."""
     import numpy as np
-    k = min(k, len(tn), len(t1))
-    same = [t.step_is_successful for t in tn[:k]] == [t.step_is_successful for t in t1[:k]]
-    cn, c1 = np.array([t.cost for t in tn[:k]]), np.array([t.cost for t in t1[:k]])
-    rel = float(np.max(np.abs(cn - c1) / np.abs(c1))) if k else 0.0
-    return bool(same and rel <= 1e-9), rel, k
+    n = min(len(tn), len(t1))
+    cn, c1 = np.array([t.cost for t in tn[:n]]), np.array([t.cost for t in t1[:n]])
+    rel = np.abs(cn - c1) / np.abs(c1)
+    same = [a.step_is_successful == b.step_is_successful for a, b in zip(tn[:n], t1[:n])]
+    agree = 0
+    while agree < n and same[agree] and rel[agree] <= 1e-9:
+        agree += 1
+    k = min(k, n)
+    return bool(all(same[:k]) and (rel[:k] <= 1e-9).all()), float(rel[:k].max()) if k else 0.0, k, agree, float(rel.max()) if n else 0.0
 
 
 def main():
@@ -190,7 +199,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--lm-iters", type=int, default=50, help="LM iterations of the full-solve measurement (0 = skip)")
-    ap.add_argument("--lm-seconds", type=float, default=90.0, help="time cap of the full solve when N>1 (weak scaling)")
+    ap.add_argument("--lm-seconds", type=float, default=60.0, help="time cap of the full solve when N>1 (weak scaling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank check and the strong-scaling leg")
     a = ap.parse_args()
@@ -271,12 +280,18 @@ def main():
             with D.Solver(graph, dcs_on=True, device=local_rank, max_num_iterations=k_iters) as ref:
                 c1, g1 = ref.linearize(graph.pose_xyt)
                 x1, s1, t1 = ref.solve()
-            ok_tr, cost_tr_rel, k = compare_traces(trace_multi, t1, k_iters + 1)
-            final_n = final_multi if k_iters >= len(trace_multi) - 1 else trace_multi[min(k_iters, len(trace_multi) - 1)].cost
+            full = k_iters >= len(trace_multi) - 1
+            gate = min(k_iters, PARITY_FULL_ITERS) if full else k_iters
+            ok_tr, cost_tr_rel, k, agree, rel_all = compare_traces(trace_multi, t1, gate + 1)
+            final_n = final_multi if full else trace_multi[min(k_iters, len(trace_multi) - 1)].cost
             out = {"cost_rel": abs(cost_n - c1) / c1, "grad_rel_max": float(np.abs(grad_n - g1).max() / np.abs(g1).max()),
                    "lm_trace_equal": ok_tr, "lm_trace_cost_rel_max": cost_tr_rel, "lm_iterations_compared": k - 1,
+                   "lm_iterations_solved": k_iters, "leading_iterations_agreeing_1e-9": agree - 1, "cost_rel_max_all_iterations": rel_all,
                    "final_cost_rel": abs(final_n - s1.final_cost) / s1.final_cost, "n_ranks": world, "n_poses": graph.n_poses}
-            out["ok"] = bool(out["cost_rel"] <= 1e-12 and out["grad_rel_max"] <= 1e-11 and ok_tr and out["final_cost_rel"] <= 1e-9)
+            # gate: linearisation at the start, the compared leading iterations to 1e-9; a full 50-iteration trajectory
+            # is additionally required to end within 1e-3 (see PARITY_FULL_ITERS above for why not 1e-9)
+            out["ok"] = bool(out["cost_rel"] <= 1e-12 and out["grad_rel_max"] <= 1e-11 and ok_tr
+                             and out["final_cost_rel"] <= (1e-3 if (full and k_iters > PARITY_FULL_ITERS) else 1e-9))
         barrier()
         return out
 

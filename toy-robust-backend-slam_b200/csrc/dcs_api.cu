@@ -28,6 +28,7 @@ using namespace dcs;
 namespace {
 
 thread_local std::string g_err;
+thread_local int64_t t_launches = 0;   // this thread's share (sizes a captured graph's launch count)
 std::atomic<int64_t> g_launches{0};    // dcs_solve_batch drives several handles from several host threads
 
 #define CK(call)                                                                                 \
@@ -54,7 +55,7 @@ std::atomic<int64_t> g_launches{0};    // dcs_solve_batch drives several handles
 #define LAUNCH(kernel, grid, block, stream, ...)                                                 \
   do {                                                                                           \
     kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                       \
-    ++g_launches;                                                                                \
+    ++g_launches; ++t_launches;                                                                  \
   } while (0)
 
 template <typename T>
@@ -197,6 +198,8 @@ struct dcs_handle {
   int dev = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // multi-rank: the halo push runs here while the SpMV's local pass runs on `stream`
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // partition (world == 1: everything)
   int rank = 0, world = 1;
@@ -216,6 +219,7 @@ struct dcs_handle {
   DevBuf<int32_t> scan_ws;      // block totals of the K0 scans (all recursion levels)
   DevBuf<int32_t> row_ptr, slot, up_flag, up_scan, block_src, task_tile0, task_obase;
   DevBuf<uint32_t> rank_info;
+  DevBuf<int32_t> rank_nloc;    // per stored row: half-edges whose column is on this rank (they come first in the row)
   DevBuf<uint4> rowinfo;        // per stored row: degree + the words of rounds 0 and 1
   DevBuf<int2> task_info;       // per task: first tile, first compact owner-block index
   int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
@@ -253,6 +257,14 @@ struct dcs_handle {
   const double4 *ipc_xa = nullptr, *ipc_xb = nullptr;       // the pose buffers as they were when the handles were exchanged
   std::vector<void*> ipc_opened;
   DevBuf<float> barrier_buf;
+  DevBuf<XchgBuf> xchg;                    // this rank's scalar-exchange buffer (peers store into it over NVLink)
+  XchgPeers xchg_peers = {};
+  int push_per_thread = 4;                 // halo entries per thread of k_halo_push (DCS_PUSH_PER_THREAD = 1 | 2 | 4)
+  bool overlap_halo = false;               // DCS_OVERLAP=1: SpMV in two passes (local columns, then halo columns) around the halo push
+                                           // on a second stream.  Off by default: measured at 2 x 1M poses the two short passes cost
+                                           // 40 us more than the one-pass product, the push they hide is 18 us (profiles/r02_multigpu.md)
+  bool xchg_ok = false;                    // peer-memory scalar all-reduce / barrier available (else ncclAllReduce)
+  int64_t pcg_graph_launches = 0;          // kernel launches inside one replay of the PCG graph
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
@@ -342,23 +354,34 @@ int bits_for(int32_t n) { int b = 1; while ((1ll << b) < (long long)n) ++b; retu
 
 int allreduce_sum(dcs_handle* h, double* d, int count) {
   if (h->world == 1) return DCS_OK;
+  if (h->xchg_ok && count <= kXchgVals) {
+    LAUNCH(k_xchg_sum, 1, 32, h->stream, h->xchg_peers, d, count);
+    return DCS_OK;
+  }
   CKN(nccl_api().AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
   return DCS_OK;
 }
 // Halo exchange of a locally indexed double4 array ([own rows | halo]) whose own rows just changed: every rank packs
 // the own entries its peers reference; grouped ncclSend/ncclRecv over NVLink move them straight into the peers' halo
 // regions (the halo is stored in global order, i.e. grouped by owner, so no unpack pass is needed).
-int halo_exchange(dcs_handle* h, double4* arr) {
+int halo_exchange(dcs_handle* h, double4* arr, cudaStream_t st = nullptr) {
   if (h->world == 1) return DCS_OK;
+  if (!st) st = h->stream;
   const int32_t ns = h->halo_send_off[h->world];
   if (h->halo_push && (arr == h->p4.p || arr == h->ipc_xa || arr == h->ipc_xb)) {
     // every rank takes the same accept/reject decisions, so "my buffer A" is "buffer A" on every peer
     const HaloPeers& P = (arr == h->p4.p) ? h->peers_p4 : (arr == h->ipc_xa ? h->peers_xa : h->peers_xb);
-    if (ns > 0) LAUNCH(k_halo_push, cdiv(ns, 256 * kPushPerThread), 256, h->stream, arr, h->halo_send_idx.p, ns, P);
+    if (ns > 0) {
+      if (h->push_per_thread == 1) LAUNCH(k_halo_push<1>, cdiv(ns, 256), 256, st, arr, h->halo_send_idx.p, ns, P);
+      else if (h->push_per_thread == 2) LAUNCH(k_halo_push<2>, cdiv(ns, 512), 256, st, arr, h->halo_send_idx.p, ns, P);
+      else LAUNCH(k_halo_push<4>, cdiv(ns, 1024), 256, st, arr, h->halo_send_idx.p, ns, P);
+    }
     // every rank's pushes have landed once all ranks passed this point of their streams
-    CKN(nccl_api().AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, h->stream));
+    if (h->xchg_ok) LAUNCH(k_xchg_sum, 1, 32, st, h->xchg_peers, (double*)nullptr, 0);
+    else CKN(nccl_api().AllReduce(h->barrier_buf.p, h->barrier_buf.p, 1, ncclFloat, ncclSum, h->comm, st));
     return DCS_OK;
   }
+  st = h->stream;     // the NCCL send/recv fallback stays on the main stream
   if (ns > 0) LAUNCH(k_halo_pack, cdiv(ns, 256), 256, h->stream, arr, h->halo_send_idx.p, ns, h->halo_send_buf.p);
   CKN(nccl_api().GroupStart());
   for (int r = 0; r < h->world; ++r) {
@@ -381,7 +404,10 @@ int setup_halo_push(dcs_handle* h) {
   cudaStream_t st = h->stream;
   const char* mode = std::getenv("DCS_HALO");
   int ok = (!(mode && std::strcmp(mode, "nccl") == 0)) ? 1 : 0;
-  struct Pair { cudaIpcMemHandle_t p4, xa, xb; };
+  struct Pair { cudaIpcMemHandle_t p4, xa, xb, xc; };
+  CK(h->xchg.alloc_zero(1, h->stream));
+  const char* smode = std::getenv("DCS_SCALARS");        // DCS_SCALARS=nccl: keep ncclAllReduce for the scalars / barrier
+  const bool want_xchg = !(smode && std::strcmp(smode, "nccl") == 0);
   std::vector<Pair> all((size_t)W);
   DevBuf<unsigned char> d_all;
   CK(d_all.alloc(sizeof(Pair) * (size_t)W));
@@ -389,7 +415,7 @@ int setup_halo_push(dcs_handle* h) {
   std::memset(&mine, 0, sizeof(mine));
   if (ok) {
     if (cudaIpcGetMemHandle(&mine.p4, h->p4.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.xa, h->xyt.p) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine.xb, h->cand_xyt.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        cudaIpcGetMemHandle(&mine.xb, h->cand_xyt.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.xc, h->xchg.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
   CK(cudaMemcpyAsync(d_all.p + sizeof(Pair) * (size_t)h->rank, &mine, sizeof(Pair), cudaMemcpyHostToDevice, st));
   CKN(nccl_api().AllGather(d_all.p + sizeof(Pair) * (size_t)h->rank, d_all.p, sizeof(Pair), ncclChar, h->comm, st));
@@ -398,6 +424,8 @@ int setup_halo_push(dcs_handle* h) {
   h->ipc_xa = h->xyt.p; h->ipc_xb = h->cand_xyt.p;
   HaloPeers P4 = {}, PA = {}, PB = {};
   P4.world = PA.world = PB.world = W;
+  XchgPeers XP = {};
+  XP.world = W; XP.rank = h->rank; XP.buf[h->rank] = h->xchg.p;
   static_assert(sizeof(P4.send_off) / sizeof(P4.send_off[0]) == kMaxWorld + 1 && sizeof(P4.ptr) / sizeof(P4.ptr[0]) == kMaxWorld,
                 "HaloPeers is sized for kMaxWorld ranks");
   if (W > kMaxWorld) { g_err = "setup_halo_push: world exceeds kMaxWorld"; return DCS_ERR_ARG; }   // dcs_create rejects it first
@@ -411,6 +439,10 @@ int setup_halo_push(dcs_handle* h) {
     h->ipc_opened.push_back(b);
     if (cudaIpcOpenMemHandle(&c, all[r].xb, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
     h->ipc_opened.push_back(c);
+    void* d = nullptr;
+    if (cudaIpcOpenMemHandle(&d, all[r].xc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    h->ipc_opened.push_back(d);
+    XP.buf[r] = static_cast<XchgBuf*>(d);
     P4.ptr[r] = static_cast<double4*>(a);
     PA.ptr[r] = static_cast<double4*>(b);
     PB.ptr[r] = static_cast<double4*>(c);
@@ -426,7 +458,13 @@ int setup_halo_push(dcs_handle* h) {
   CK(cudaStreamSynchronize(st));
   h->halo_push = (flag == 0.f);
   h->peers_p4 = P4; h->peers_xa = PA; h->peers_xb = PB;
-  if (h->opt.verbose && h->rank == 0) std::fprintf(stderr, "[dcs] halo exchange: %s\n", h->halo_push ? "peer-memory push (CUDA IPC over NVLink)" : "ncclSend/ncclRecv");
+  h->xchg_peers = XP;
+  if (const char* ppt = std::getenv("DCS_PUSH_PER_THREAD")) h->push_per_thread = std::atoi(ppt);
+  if (const char* ov = std::getenv("DCS_OVERLAP")) h->overlap_halo = std::atoi(ov) != 0;
+  h->xchg_ok = h->halo_push && want_xchg;     // DCS_SCALARS must be set the same on every rank
+  if (h->opt.verbose && h->rank == 0)
+    std::fprintf(stderr, "[dcs] halo exchange: %s; scalars: %s\n", h->halo_push ? "peer-memory push (CUDA IPC over NVLink)" : "ncclSend/ncclRecv",
+                 h->xchg_ok ? "peer-memory flags" : "ncclAllReduce");
   return DCS_OK;
 }
 
@@ -554,7 +592,7 @@ int linearize_sc(dcs_handle* h, const double4* xyt, double inv_radius, int reduc
          h->Hdiag.p, h->grad.p, h->task_part.p);
   if (!reduce) {
     k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-    ++g_launches;
+    ++g_launches; ++t_launches;
   }
   h->have_lin = true;
   h->mirrored = false;
@@ -567,7 +605,7 @@ int linearize(dcs_handle* h, const double4* xyt) {
   LAUNCH(k_linearize, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->P, h->n_loc, h->Hup.p, h->Hdiag.p,
          h->grad.p, h->task_part.p);
   k_fold_tasks<2, 1><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_COST, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-  ++g_launches;
+  ++g_launches; ++t_launches;
   if (h->world > 1) {   // one collective: every rank's (cost, |g|^2, |g|_inf); folded on the host in rank order
     CKN(nccl_api().AllGather(h->scal.p + S_COST, h->rank_scal.p, 4, ncclDouble, h->comm, h->stream));
     h->lin_scal_pending = true;
@@ -607,29 +645,51 @@ int cost_only(dcs_handle* h, const double4* xyt, int slot, const double* sw = nu
   }
   LAUNCH(k_cost_rows, h->nblk, kRowsPerBlock, h->stream, xyt, h->layout(), h->recs.p, h->P, h->n_loc, h->task_part.p);
   k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + slot, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-  ++g_launches;
+  ++g_launches; ++t_launches;
   CKS(allreduce_sum(h, h->scal.p + slot, 1));
   return DCS_OK;
 }
 
-// one PCG iteration on the stream (capturable)
+// q = (off-diagonal blocks + D) p over the rank's rows, p.q -> scal[out_slot] (summed over ranks).  p's own rows are
+// current; with several ranks the halo entries are fetched here: the peers' pushes (second stream) overlap the pass
+// over the local columns, the halo columns follow once every rank's pushes have landed.  Capturable.
+int spmv_product(dcs_handle* h, const double* D, int out_slot, int rotate_rz) {
+  cudaStream_t st = h->stream;
+  if (h->world == 1) {
+    LAUNCH((k_spmv<double, kSpmvAll>), h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
+  } else if (h->halo_push && h->overlap_halo) {
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    CKS(halo_exchange(h, h->p4.p, h->stream2));
+    CK(cudaEventRecord(h->ev_join, h->stream2));
+    LAUNCH((k_spmv<double, kSpmvLocal>), h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    LAUNCH((k_spmv<double, kSpmvHalo>), h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
+  } else {
+    CKS(halo_exchange(h, h->p4.p));
+    LAUNCH((k_spmv<double, kSpmvAll>), h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
+  }
+  k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + out_slot, h->scal.p, rotate_rz, h->fold_ws.p, h->tickets.p + 6);
+  ++g_launches; ++t_launches;
+  CKS(allreduce_sum(h, h->scal.p + out_slot, 1));
+  return DCS_OK;
+}
+
+// one PCG iteration on the stream (capturable).  Starts with the halo exchange of the direction the previous
+// iteration (or the initialisation) left in the own rows of p.
 int pcg_iteration(dcs_handle* h, const double* D) {
-  LAUNCH(k_spmv<double>, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
-  k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1, h->fold_ws.p, h->tickets.p + 6);
-  ++g_launches;
-  CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
+  CKS(spmv_product(h, D, S_PQ, 1));
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
            h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-    ++g_launches;
+    ++g_launches; ++t_launches;
   } else {
     LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, 0, h->nrows, h->ldn, h->w.p,
            h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
   }
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
   LAUNCH(k_pcg_direction, h->vec_grid(), kVecThreads, h->stream, h->z.p, 0, h->nrows, h->ldn, h->p4.p, h->scal.p);
-  CKS(halo_exchange(h, h->p4.p));
   return DCS_OK;
 }
 
@@ -646,14 +706,13 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
     LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->perm.p, 0, h->nrows,
            h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-    ++g_launches;
+    ++g_launches; ++t_launches;
   } else
   LAUNCH(k_pcg_init, h->vec_grid(), kVecThreads, h->stream, rhs, h->Minv.p, h->is_free.p, 0, h->nrows, h->ldn, h->w.p, h->r.p,
          h->z.p, h->p4.p, h->partials.p, h->tickets.p + 4, h->scal.p);
   CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
   LAUNCH(k_pcg_init_finish, 1, 1, h->stream, h->scal.p);
-  CKS(halo_exchange(h, h->p4.p));
-  CKS(read_scalars(h));
+  CKS(read_scalars(h));       // (the halo of p is fetched by the first product)
   const double rr0 = h->h_scal[S_RR0];
   int iters = 0;
   double rr = rr0;
@@ -662,6 +721,7 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
     if (!h->pcg_graph || h->pcg_graph_iters != batch || h->pcg_graph_D != h->Adiag.p) {
       if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
       cudaGraph_t g = nullptr;
+      const int64_t launches_before = t_launches;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       int st = DCS_OK;
       for (int i = 0; i < batch && st == DCS_OK; ++i) st = pcg_iteration(h, h->Adiag.p);
@@ -672,12 +732,13 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
       CK(cudaGraphDestroy(g));
       h->pcg_graph_iters = batch;
       h->pcg_graph_D = h->Adiag.p;
-      g_launches -= (h->opt.preconditioner == 1 ? 5LL : 4LL) * batch;   // capture does not launch
+      h->pcg_graph_launches = t_launches - launches_before;      // capture does not launch: counted per replay
+      g_launches -= h->pcg_graph_launches;
     }
     const double target = h->opt.pcg_rel_tol * h->opt.pcg_rel_tol * rr0;
     while (iters < h->opt.pcg_max_iter) {
       CK(cudaGraphLaunch(h->pcg_graph, h->stream));
-      g_launches += (h->opt.preconditioner == 1 ? 5LL : 4LL) * batch;
+      g_launches += h->pcg_graph_launches;
       iters += batch;
       CKS(read_scalars(h));
       rr = h->h_scal[S_RR];
@@ -784,6 +845,9 @@ void dcs_destroy(dcs_handle* h) {
   if (h->h_pin3) cudaFreeHost(h->h_pin3);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -831,6 +895,9 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   h->sc = o->switchable_on != 0; h->sc_lambda = o->switch_prior_lambda;
   if (h->rank < 0 || h->rank >= h->world) { g_err = "dcs_create: bad rank"; return DCS_ERR_ARG; }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   cudaStream_t st = h->stream;
@@ -907,8 +974,9 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     LAUNCH(k_row_ptr, cdiv(rows + 1, 256), 256, st, h->keys.p, nh, h->row_lo, rows, h->row_ptr.p);
   }
   CK(h->rank_of.alloc((size_t)h->ldn)); CK(h->perm.alloc((size_t)h->ldn));
-  CK(h->rank_info.alloc((size_t)h->ldn));
-  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->rank_of.p, h->perm.p, h->rank_info.p);
+  CK(h->rank_info.alloc((size_t)h->ldn)); CK(h->rank_nloc.alloc((size_t)h->ldn));
+  LAUNCH(k_jds_rank, h->nwin, kWindow, st, h->row_ptr.p, h->keys.p, (int32_t)h->ldn, h->world > 1 ? 1 : 0, h->rank_of.p, h->perm.p,
+         h->rank_info.p, h->rank_nloc.p);
   // per-row arrays live in (window, rank) order from here on
   if (h->nrows > 0) LAUNCH(k_is_free, cdiv(h->nrows, 256), 256, st, h->deg_all.p, h->row_lo, h->nrows, h->fixed, h->rank_of.p, h->is_free.p);
   // SELL tiles: a task's tile count = its largest degree (first lane: ranks are degree-sorted); tile0 = exclusive scan
@@ -944,12 +1012,12 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
       LAUNCH(k_mirror_src, cdiv(nh, 256), 256, st, h->vals.p, h->slot.p, nh, h->cols.p, edge_slot.p, mirror_src.p);
     }
     // compact owner-block order = the order k_linearize meets the owner half-edges in
-    LAUNCH(k_task_walk<false>, h->ntasks, kRowsPerBlock, st, h->ntasks, h->rank_info.p, h->task_tile0.p, (const int32_t*)nullptr,
+    LAUNCH(k_task_walk<false>, h->ntasks, kRowsPerBlock, st, h->ntasks, h->rank_info.p, h->rank_nloc.p, h->task_tile0.p, (const int32_t*)nullptr,
            h->cols.p, h->task_obase.p, (int32_t*)nullptr, (HalfEdgeRec*)nullptr, (uint4*)nullptr);
     CKS(scan_exclusive(h->task_obase.p, (int64_t)h->ntasks + 1, st, h->scan_ws.p, h->scan_ws.n));
     int32_t n_own = 0;
     CK(cudaMemcpyAsync(&n_own, h->task_obase.p + h->ntasks, 4, cudaMemcpyDeviceToHost, st));
-    LAUNCH(k_task_walk<true>, h->ntasks, kRowsPerBlock, st, h->ntasks, h->rank_info.p, h->task_tile0.p, h->task_obase.p, h->cols.p,
+    LAUNCH(k_task_walk<true>, h->ntasks, kRowsPerBlock, st, h->ntasks, h->rank_info.p, h->rank_nloc.p, h->task_tile0.p, h->task_obase.p, h->cols.p,
            (int32_t*)nullptr, cidx.p, h->recs.p, h->rowinfo.p);
     LAUNCH(k_task_info, cdiv(h->ntasks + 1, 256), 256, st, h->ntasks, h->task_tile0.p, h->task_obase.p, h->task_info.p);
     if (nh > 0) LAUNCH(k_block_src, cdiv(nh, 256), 256, st, h->cols.p, h->slot.p, mirror_src.p, cidx.p, nh, h->block_src.p);
@@ -1346,12 +1414,8 @@ int dcs_solve(dcs_handle* h, double* pose_xyt_inout, dcs_summary* sum, dcs_itera
     LAUNCH(k_pack_step, h->vec_grid(), kVecThreads, st, h->w.p, grad_full, 0, h->nrows, h->ldn, h->p4.p, h->partials.p,
            h->tickets.p + 4, h->scal.p);
     CKS(allreduce_sum(h, h->scal.p + S_WG, 1));
-    CKS(halo_exchange(h, h->p4.p));
     CKS(ensure_mirror(h));
-    LAUNCH(k_spmv<double>, h->nblk, kRowsPerBlock, st, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, h->Hdiag.p, h->n_loc, h->q.p, h->task_part.p);
-    k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, st>>>(h->task_part.p, h->nblk, h->scal.p + S_WHW, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-    ++g_launches;
-    CKS(allreduce_sum(h, h->scal.p + S_WHW, 1));
+    CKS(spmv_product(h, h->Hdiag.p, S_WHW, 0));
     // true residual |(H + Lambda) w - g| / |g| of this step's linear solve, from q = H w just formed
     LAUNCH(k_true_residual, h->vec_grid(), kVecThreads, st, h->grad.p, h->q.p, h->w.p, h->lmdiag.p, h->scale.p, h->is_free.p,
            h->nrows, h->ldn, 1.0 / radius, h->partials.p, h->tickets.p + 4, h->scal.p);

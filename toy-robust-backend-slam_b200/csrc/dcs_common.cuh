@@ -19,7 +19,9 @@ constexpr int kK1Rounds = 2;             // rounds per pipeline stage of k_linea
                                          // word of the round kK1Rounds later (baked into the data by the pattern build)
 constexpr int kTailTiles = 4;            // zero tiles after the last task (prefetch addresses are clamped, this is slack)
 constexpr uint32_t kKeyNonOwner = 1u << 27;  // sort-key bit just above the 27 column bits: non-owner half-edges follow a
-                                             // row's owner ones (the radix sort covers bits 0..27 of the column word)
+                                             // row's owner ones (the radix sort covers bits 0..31 of the column word)
+constexpr uint32_t kKeyHalo = 1u << 28;      // multi-rank: half-edges whose column lives on another rank sort LAST in their
+                                             // row, so the SpMV can do the local columns while the halo is still in flight
 constexpr uint32_t kIdxMask = 0x07FFFFFFu;  // low 27 bits of a half-edge word: other pose (<= 134M poses)
 constexpr uint32_t kFlagSideB = 1u << 31;   // row pose is the edge's second endpoint (Edge::b)
 constexpr uint32_t kFlagDcs = 1u << 30;     // DCS functor applies (loop/bogus edge and METHOD 1)

@@ -102,7 +102,7 @@ DCS_API int dcs_debug_pcg_stages(dcs_handle* h, int repeats, double* out6) {
   const double* D = h->Adiag.p;
   for (int it = 0; it < repeats + 3; ++it) {
     cudaEventRecord(ev[0], h->stream);
-    LAUNCH(k_spmv<double>, h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
+    LAUNCH((k_spmv<double, kSpmvAll>), h->nblk, kRowsPerBlock, h->stream, h->p4.p, h->layout(), h->cols.p, h->Hoff.p, D, h->n_loc, h->q.p, h->task_part.p);
     k_fold_tasks<1, 0><<<fold_blocks(h->nblk), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->nblk, h->scal.p + S_PQ, h->scal.p, 1, h->fold_ws.p, h->tickets.p + 6);
     cudaEventRecord(ev[1], h->stream);
     CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));

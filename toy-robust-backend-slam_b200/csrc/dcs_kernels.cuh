@@ -36,7 +36,8 @@ struct RowLayout {
   int64_t ldn;               // leading dimension of per-row SoA arrays
   int64_t ldh;               // slots = 32 * (tiles + kTailTiles)
   int64_t ldu;               // compact owner-block capacity (multiple of 32)
-  const uint4* rowinfo;      // [ldn] per stored row: (degree, word of round 0, word of round 1, 0)
+  const uint4* rowinfo;      // [ldn] per stored row: (degree, word of round 0, word of round 1, local entries: the first
+                             // rowinfo.w half-edges of the row have their column on this rank)
   const int2* task_info;     // [ntasks + 1] (first tile, first compact owner-block index)
 };
 
@@ -325,8 +326,8 @@ k_fold_tasks(const double* __restrict__ part, int n, double* out, double* scal, 
 //                   (word of the same row kK1Rounds rounds later); rowinfo (degree + the words of rounds 0 and 1)
 template <bool kWrite>
 __global__ void __launch_bounds__(kRowsPerBlock)
-k_task_walk(int32_t ntasks, const uint32_t* __restrict__ rank_info, const int32_t* __restrict__ tile0, const int32_t* __restrict__ obase,
-            const uint32_t* __restrict__ cols, int32_t* own_cnt, int32_t* cidx, HalfEdgeRec* recs, uint4* rowinfo) {
+k_task_walk(int32_t ntasks, const uint32_t* __restrict__ rank_info, const int32_t* __restrict__ rank_nloc, const int32_t* __restrict__ tile0,
+            const int32_t* __restrict__ obase, const uint32_t* __restrict__ cols, int32_t* own_cnt, int32_t* cidx, HalfEdgeRec* recs, uint4* rowinfo) {
   const int task = blockIdx.x, lane = threadIdx.x & 31;
   if (task >= ntasks) return;
   const int m = task * kSlice + lane;
@@ -344,7 +345,7 @@ k_task_walk(int32_t ntasks, const uint32_t* __restrict__ rank_info, const int32_
     }
     run += __popc(om);
   }
-  if (kWrite) rowinfo[m] = make_uint4((uint32_t)deg, deg > 0 ? cols[s0] : 0u, deg > 1 ? cols[s0 + kSlice] : 0u, 0u);
+  if (kWrite) rowinfo[m] = make_uint4((uint32_t)deg, deg > 0 ? cols[s0] : 0u, deg > 1 ? cols[s0 + kSlice] : 0u, (uint32_t)rank_nloc[m]);
   else if (lane == 0) own_cnt[task] = run;
 }
 __global__ void k_task_kmax(int32_t ntasks, const uint32_t* __restrict__ rank_info, int32_t* kmax) {
@@ -570,7 +571,12 @@ __device__ __forceinline__ double ld_blockval(const float* p, uint64_t pol) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
   return (double)v;
 }
-template <typename T>
+// Multi-rank: a row's half-edges are stored local columns first, halo columns last (kKeyHalo), so the product runs
+// in two passes of the same kernel over disjoint round ranges: kSpmvLocal (diagonal block + rounds [0, nloc), needs no
+// halo entry of p: it runs while the peers' pushes are in flight) and kSpmvHalo (rounds [nloc, degree) added to q, then
+// the p.q partial).  Single rank: kSpmvAll.
+enum { kSpmvAll = 0, kSpmvLocal = 1, kSpmvHalo = 2 };
+template <typename T, int kPass>
 __global__ void __launch_bounds__(kRowsPerBlock)
 k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__ cols, const T* __restrict__ Hoff,
        const double* __restrict__ D, int32_t n_loc, double* __restrict__ q, double* __restrict__ task_part) {
@@ -580,18 +586,23 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
   const int lr = task * kSlice + lane;
   double y0 = 0, y1 = 0, y2 = 0, dot = 0;
   if (lr < L.nrows) {
-    const int deg = (int)L.rowinfo[lr].x;
+    const uint4 info = L.rowinfo[lr];
+    const int deg = kPass == kSpmvLocal ? (int)info.w : (int)info.x;
     const int64_t tile0 = L.task_info[task].x;
     const double4 p = ld_keep4(p4 + lr, pol.keep);
-    const double a00 = D[0 * L.ldn + lr], a01 = D[1 * L.ldn + lr], a02 = D[2 * L.ldn + lr];
-    const double a11 = D[3 * L.ldn + lr], a12 = D[4 * L.ldn + lr], a22 = D[5 * L.ldn + lr];
-    y0 = fma(a00, p.x, fma(a01, p.y, a02 * p.z));
-    y1 = fma(a01, p.x, fma(a11, p.y, a12 * p.z));
-    y2 = fma(a02, p.x, fma(a12, p.y, a22 * p.z));
+    if (kPass == kSpmvHalo) {
+      y0 = q[0 * L.ldn + lr]; y1 = q[1 * L.ldn + lr]; y2 = q[2 * L.ldn + lr];
+    } else {
+      const double a00 = D[0 * L.ldn + lr], a01 = D[1 * L.ldn + lr], a02 = D[2 * L.ldn + lr];
+      const double a11 = D[3 * L.ldn + lr], a12 = D[4 * L.ldn + lr], a22 = D[5 * L.ldn + lr];
+      y0 = fma(a00, p.x, fma(a01, p.y, a02 * p.z));
+      y1 = fma(a01, p.x, fma(a11, p.y, a12 * p.z));
+      y2 = fma(a02, p.x, fma(a12, p.y, a22 * p.z));
+    }
     const uint32_t* cp = cols + tile0 * kSlice + lane;       // round k: + 32 k
     const T* hp = Hoff + tile0 * 288 + lane;                 // round k: + 288 k, value c: + 32 c
     constexpr int U = 4;     // rounds in flight per thread: 4 x (9 block words + column + gathered p) loads
-    int k = 0;
+    int k = kPass == kSpmvHalo ? (int)info.w : 0;
     for (; k + U <= deg; k += U) {
       uint32_t j[U]; double h[U][9]; double4 pj[U];
 #pragma unroll
@@ -623,9 +634,11 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
     q[0 * L.ldn + lr] = y0; q[1 * L.ldn + lr] = y1; q[2 * L.ldn + lr] = y2;
     dot = fma(p.x, y0, fma(p.y, y1, p.z * y2));
   }
+  if constexpr (kPass != kSpmvLocal) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if (lane == 0) task_part[task] = dot;
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) task_part[task] = dot;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -130,8 +130,9 @@ __global__ void k_halfedge_fill(const int32_t* ea, const int32_t* eb, int32_t E,
   const int32_t a = ea[e], b = eb[e];
   int32_t o = off[e];
   auto key = [&](int32_t row, int32_t col) {
-    const bool owner = col != fixed && (row < col || col < row_lo || col >= row_hi);
-    return ((uint64_t)(uint32_t)row << 32) | (owner ? 0u : kKeyNonOwner) | (uint32_t)col;
+    const bool halo = col < row_lo || col >= row_hi;
+    const bool owner = col != fixed && (row < col || halo);
+    return ((uint64_t)(uint32_t)row << 32) | (halo ? kKeyHalo : 0u) | (owner ? 0u : kKeyNonOwner) | (uint32_t)col;
   };
   if (a != fixed && a >= row_lo && a < row_hi) { keys[o] = key(a, b); vals[o] = ((uint32_t)e << 1); ++o; }
   if (b != fixed && b >= row_lo && b < row_hi) { keys[o] = key(b, a); vals[o] = ((uint32_t)e << 1) | 1u; }
@@ -161,18 +162,25 @@ __global__ void k_row_ptr(const uint64_t* keys, int32_t nh, int32_t row_lo, int3
 // 86% at 128), its k-th half-edges are one 32-slot tile, its tiles are consecutive (see RowLayout).
 // pass 1: rank of each row inside its window
 __global__ void __launch_bounds__(kWindow)
-k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t* rank_of, uint16_t* perm, uint32_t* rank_info) {
+k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, int by_local, uint16_t* rank_of, uint16_t* perm,
+           uint32_t* rank_info, int32_t* rank_nloc) {
   __shared__ int32_t s_deg[kWindow];
   __shared__ int32_t s_own[kWindow];
   const int32_t r = blockIdx.x * kWindow + threadIdx.x;
-  int32_t d = 0, own = 0;
+  int32_t d = 0, own = 0, nloc = 0;
   if (r < nrows) {
     const int32_t b = row_ptr[r], e = row_ptr[r + 1];
     d = e - b;
-    // a row's entries are sorted owner-first: own = how many have the non-owner key bit clear
+    // a row's entries are sorted [local owner | local non-owner | halo (owners)]: nloc = entries with the halo bit clear
     int32_t lo = b, hi = e;
+    while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (keys[mid] & kKeyHalo) hi = mid; else lo = mid + 1; }
+    nloc = lo - b;
+    // own = how many carry the non-owner key bit clear (inside the local part the bit is monotone)
+    lo = b; hi = b + nloc;
     while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (keys[mid] & kKeyNonOwner) hi = mid; else lo = mid + 1; }
-    own = lo - b;
+    own = (lo - b) + (d - nloc);
+    if (by_local) own = nloc;      // multi-rank: second ranking key = local entries, so that in every tile of a task the
+                                   // local lanes are a prefix and the halo lanes a suffix (k_spmv's two passes)
   }
   s_deg[threadIdx.x] = d;
   s_own[threadIdx.x] = own;
@@ -189,6 +197,7 @@ k_jds_rank(const int32_t* row_ptr, const uint64_t* keys, int32_t nrows, uint16_t
   perm[(int64_t)blockIdx.x * kWindow + rank] = (uint16_t)threadIdx.x;
   // what a warp task needs to start, in one coalesced word per rank: local row (10 bits) | degree
   rank_info[(int64_t)blockIdx.x * kWindow + rank] = ((uint32_t)d << 10) | (uint32_t)threadIdx.x;
+  rank_nloc[(int64_t)blockIdx.x * kWindow + rank] = nloc;
 }
 // pass 2: sorted CSR position -> SELL slot = (first tile of the row's task + k) * 32 + lane
 __global__ void k_sell_slot(const uint64_t* keys, int32_t nh, int32_t row_lo, const int32_t* row_ptr,
@@ -251,7 +260,7 @@ struct HaloPeers {
   int32_t dst_base[kMaxWorld];       // first halo entry in the peer's array that belongs to this rank
   int32_t world;
 };
-constexpr int kPushPerThread = 4;
+template <int kPushPerThread>
 __global__ void __launch_bounds__(256)
 k_halo_push(const double4* __restrict__ arr, const int32_t* __restrict__ idx, int32_t n, HaloPeers P) {
   const int32_t j0 = blockIdx.x * (256 * kPushPerThread) + threadIdx.x;
@@ -259,7 +268,7 @@ k_halo_push(const double4* __restrict__ arr, const int32_t* __restrict__ idx, in
 #pragma unroll
   for (int u = 0; u < kPushPerThread; ++u) {          // all gathers first (local L2), then the remote stores
     const int32_t j = j0 + u * 256;
-    if (j < n) v[u] = arr[idx[j]];
+    if (j < n) asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[u].x), "=d"(v[u].y), "=d"(v[u].z), "=d"(v[u].w) : "l"(arr + idx[j]));
   }
 #pragma unroll
   for (int u = 0; u < kPushPerThread; ++u) {
@@ -268,7 +277,59 @@ k_halo_push(const double4* __restrict__ arr, const int32_t* __restrict__ idx, in
     int r = 0;
 #pragma unroll
     for (int q = 1; q < kMaxWorld; ++q) r += (q < P.world && j >= P.send_off[q]) ? 1 : 0;
-    P.ptr[r][P.dst_base[r] + (j - P.send_off[r])] = v[u];
+    // ONE 256-bit store per entry: a warp writes 32 whole 32-byte sectors (1 KB contiguous in the peer's halo region).
+    // A plain double4 assignment compiles to two 128-bit stores, i.e. two half-sector write packets per entry on NVLink.
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(P.ptr[r] + P.dst_base[r] + (j - P.send_off[r])), "d"(v[u].x), "d"(v[u].y),
+                 "d"(v[u].z), "d"(v[u].w) : "memory");
+  }
+}
+
+// Scalar all-reduce / barrier over NVLink peer memory (replaces ncclAllReduce of 1-4 doubles inside the PCG iteration:
+// a 10-17 us collective launch for 8-32 bytes).  Every rank owns one XchgBuf (CUDA IPC, opened by all peers).  An
+// exchange = one tiny kernel per rank: store my partial values into slot [epoch parity][my rank] of EVERY rank's buffer,
+// fence, publish the epoch in that rank's flag word for me (release, system scope); then spin (acquire) until all
+// ranks' flags in MY buffer carry the epoch and add their values in rank order - the same order on every rank, so the
+// sums are bit-identical everywhere.  All ranks issue the same exchanges in the same stream order, so one running
+// epoch serves every call site; a rank can run at most one exchange ahead of a peer (finishing exchange e+1 needs the
+// peer's flag e+1, which the peer publishes after it has read epoch e), so two value slots by epoch parity suffice.
+// count = 0 is a barrier: the peer stores of earlier kernels on the stream (k_halo_push) happen before the flag.
+constexpr int kXchgVals = 4;
+struct XchgBuf {
+  double data[2][kMaxWorld][kXchgVals];
+  unsigned long long flag[kMaxWorld];
+  unsigned long long epoch;            // exchanges completed by the owner (owner-private)
+};
+struct XchgPeers { XchgBuf* buf[kMaxWorld]; int32_t world, rank; };
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(32)
+k_xchg_sum(XchgPeers X, double* vals, int count) {
+  __shared__ double s_v[kMaxWorld][kXchgVals];
+  XchgBuf* mine = X.buf[X.rank];
+  const int t = threadIdx.x;
+  const unsigned long long e = mine->epoch + 1;      // read by every lane before lane 0 advances it (after the syncwarp)
+  if (t < X.world) {
+    XchgBuf* dst = X.buf[t];
+    for (int k = 0; k < count; ++k) dst->data[e & 1][X.rank][k] = vals[k];
+    __threadfence_system();
+    st_release_sys(&dst->flag[X.rank], e);
+    while (ld_acquire_sys(&mine->flag[t]) < e) { }
+    for (int k = 0; k < count; ++k) s_v[t][k] = __ldcg(&mine->data[e & 1][t][k]);
+  }
+  __syncwarp();
+  if (t == 0) {
+    for (int k = 0; k < count; ++k) {
+      double a = 0.0;
+      for (int r = 0; r < X.world; ++r) a += s_v[r][k];
+      vals[k] = a;
+    }
+    mine->epoch = e;
   }
 }
 
