@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--lm-seconds", type=float, default=60.0, help="time cap of the full solve when N>1 (weak scaling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank check and the strong-scaling leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the METHOD 2 / batched-solve side measurements (N=1)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -390,6 +391,34 @@ def main():
                           "parity": parity_vs_single_rank(g1, s1, trace1, summ1.final_cost, len(trace1) - 1)})
         s1.close()
 
+    # ---- side measurements of the "next" rows (N=1 only): METHOD 2 on the largest real config, batched tiny solves
+    extras = None
+    if world == 1 and not a.no_extras:
+        gm = D.Graph.load_npz(os.path.join(ROOT, "tests", "golden", "M3500_100_seed1.npz"))
+        with D.Solver(gm, dcs_on=False, switchable_on=1, device=local_rank) as s2:
+            t0 = time.perf_counter()
+            _, sm2, tr2 = s2.solve()
+            dt2 = time.perf_counter() - t0
+        m2 = trace_summary(sm2, tr2, dt2)
+        m2["config"] = "METHOD 2 (switchable constraints), M3500 + 100 outlier loops, 50 LM iterations"
+        gi = D.Graph.load_npz(os.path.join(ROOT, "tests", "golden", "INTEL_50_seed1.npz"))
+        rng = np.random.default_rng(5)
+        odo, loops = np.flatnonzero(gi.kind == 0), np.flatnonzero(gi.kind != 0)
+        variants = []
+        for v in range(64):
+            keep = np.r_[odo, np.sort(rng.choice(loops, size=150 + v, replace=False))]
+            variants.append(D.Graph(gi.pose_xyt, gi.edge_a[keep], gi.edge_b[keep], gi.meas_xyt[keep], gi.kind[keep]))
+        batch = {}
+        for nt in (1, 8, 16):
+            D.solve_batch(variants[:4], dcs_on=False, n_threads=nt, max_num_iterations=2)
+            t0 = time.perf_counter()
+            sums, _ = D.solve_batch(variants, dcs_on=False, n_threads=nt, max_num_iterations=2)
+            batch[f"threads_{nt}"] = {"seconds": time.perf_counter() - t0, "solves_per_sec": len(variants) / (time.perf_counter() - t0)}
+        batch["config"] = ("dcs_solve_batch: 64 variants of INTEL (1228 poses, odometry + 150-213 loop edges each), plain residual + "
+                           "Huber, 2 LM iterations each (the layer managers' evaluate_cost shape), handle creation included")
+        batch["final_cost_first"] = sums[0].final_cost
+        extras = {"method2": m2, "batched_tiny_solves": batch}
+
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu:
         cb = cpu_baseline_block()
@@ -411,7 +440,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / a.steps, "note": "bytes per rank; every rank uploads its own pose rows"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb, "lm": lm, "parity": parity,
-        "strong_1m": strong_1m, "final_cost_check": cost}))
+        "strong_1m": strong_1m, "extras": extras, "final_cost_check": cost}))
     bad = [p for p in (parity, (strong_1m or {}).get("parity")) if p is not None and not p["ok"]]
     if bad:
         sys.stderr.write("bench.py: N-rank vs 1-rank parity FAILED: %s\n" % json.dumps(bad))

@@ -181,7 +181,7 @@ __global__ void k_export_upper(const uint64_t* __restrict__ keys, const uint32_t
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[3 * r + c] += side_b ? in[(3 * c + r) * 32] : in[(3 * r + c) * 32];
+      for (int c = 0; c < 3; ++c) acc[3 * r + c] += side_b ? in[block_plane(3 * c + r) * 32] : in[block_plane(3 * r + c) * 32];
   }
   double* o = out + 9 * (int64_t)flag_scan[i];
 #pragma unroll
@@ -223,15 +223,13 @@ struct dcs_handle {
   DevBuf<uint4> rowinfo;        // per stored row: degree + the words of rounds 0 and 1
   DevBuf<int2> task_info;       // per task: first tile, first compact owner-block index
   int64_t ldu = 32;            // compact owner-block leading dimension (owner half-edges, padded)
-  DevBuf<double> Hup;          // compact edge blocks H_ab, tile-interleaved [ldu / 32][9][32], (task, round, lane) order
+  DevBuf<double> Hup;          // compact edge blocks H_ab, tile-interleaved [ldu / 32][8][32], (task, round, lane) order
   bool mirrored = false;       // Hoff (slot order, both triangles) has been filled from Hup for the current linearization
-  bool mirrored32 = false;     // ... and its single-precision shadow
   DevBuf<uint16_t> rank_of, perm;
   int32_t n_upper = 0;
   // half-edges (SELL slot order)
   DevBuf<uint32_t> cols;        // other pose | flags: what the SpMV streams
   DevBuf<HalfEdgeRec> recs;     // 32-byte records: what k_linearize / k_cost_rows stream
-  DevBuf<float> Hoff32;         // single-precision shadow of Hoff (mixed-precision PCG only)
   // state
   DevBuf<double4> xyt, cand_xyt, p4;
   DevBuf<double> Hoff, Hdiag, grad, scale, lmdiag, Adiag, Minv, w, r, q, z, lambda_tmp, rhs_tmp;
@@ -596,7 +594,6 @@ int linearize_sc(dcs_handle* h, const double4* xyt, double inv_radius, int reduc
   }
   h->have_lin = true;
   h->mirrored = false;
-  h->mirrored32 = false;
   return DCS_OK;
 }
 
@@ -612,21 +609,12 @@ int linearize(dcs_handle* h, const double4* xyt) {
   }
   h->have_lin = true;
   h->mirrored = false;
-  h->mirrored32 = false;
   return DCS_OK;
 }
 
 // linear-solver setup: fill the slot-order block storage (both triangles) the row-wise SpMV reads from the compact
-// edge blocks; `single`: the single-precision shadow used by the mixed-precision inner iterations
-int ensure_mirror(dcs_handle* h, bool single = false) {
-  if (single) {
-    if (!h->mirrored32) {
-      if (!h->Hoff32.p) CK(h->Hoff32.alloc_zero(9 * (size_t)h->ldh, h->stream));
-      LAUNCH(k_expand<float>, cdiv(h->ldh, 256), 256, h->stream, h->block_src.p, h->cols.p, h->ldh, h->Hup.p, h->Hoff32.p);
-      h->mirrored32 = true;
-    }
-    return DCS_OK;
-  }
+// edge blocks
+int ensure_mirror(dcs_handle* h) {
   if (!h->mirrored) {
     LAUNCH(k_expand<double>, cdiv(h->ldh, 256), 256, h->stream, h->block_src.p, h->cols.p, h->ldh, h->Hup.p, h->Hoff.p);
     h->mirrored = true;
@@ -1042,7 +1030,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   const size_t LN = (size_t)h->ldn;
   const size_t NL = (size_t)std::max(h->n_loc, 1);
   CK(h->xyt.alloc_zero(NL, st)); CK(h->cand_xyt.alloc_zero(NL, st)); CK(h->p4.alloc_zero(NL, st));
-  CK(h->Hoff.alloc_zero(9 * HH, st)); CK(h->Hup.alloc_zero(9 * (size_t)h->ldu, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
+  CK(h->Hoff.alloc_zero(kBlockVals * HH, st)); CK(h->Hup.alloc_zero(kBlockVals * (size_t)h->ldu, st)); CK(h->Hdiag.alloc_zero(6 * LN, st)); CK(h->grad.alloc_zero(3 * LN, st));
   CK(h->scale.alloc_zero(3 * LN, st)); CK(h->lmdiag.alloc_zero(3 * LN, st)); CK(h->Adiag.alloc_zero(6 * LN, st)); CK(h->Minv.alloc_zero(6 * LN, st));
   CK(h->w.alloc_zero(3 * LN, st)); CK(h->r.alloc_zero(3 * LN, st)); CK(h->q.alloc_zero(3 * LN, st)); CK(h->z.alloc_zero(3 * LN, st));
   CK(h->lambda_tmp.alloc_zero(3 * LN, st)); CK(h->rhs_tmp.alloc_zero(3 * LN, st));

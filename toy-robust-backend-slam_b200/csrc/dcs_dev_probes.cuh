@@ -18,7 +18,7 @@ __global__ void k_dbg_flat(const HalfEdgeRec* __restrict__ recs, const double4* 
   if ((mode & 2) && (r.word & kFlagOwner)) {
     double* o = Hup + block_base((i >> 1) % ldu);       // ~ the compact array's footprint
 #pragma unroll
-    for (int k = 0; k < 9; ++k) st_stream(o + k * 32, a + k * b + c, pol.stream);
+    for (int k = 0; k < kBlockVals; ++k) st_stream(o + k * 32, a + k * b + c, pol.stream);
   }
   if (!(mode & 2) && a + b + c == 1.2345e300) Hup[i] = a;
 }

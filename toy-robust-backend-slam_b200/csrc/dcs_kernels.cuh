@@ -50,9 +50,15 @@ struct __align__(32) HalfEdgeRec {
                              // next pipeline stage needs no separate index stream
 };
 
-// Tile-interleaved 3x3 block arrays ([tile][9][32], T = double or float): all nine values of a lane's block sit at
-// constant offsets from one address, a warp writes / reads 9 x 256 (128) contiguous bytes of one 2304 (1152)-byte tile.
-__device__ __forceinline__ int64_t block_base(int64_t slot) { return (slot >> 5) * 288 + (slot & 31); }
+// Tile-interleaved 3x3 block arrays ([tile][8][32], T = double or float): the values of a lane's block sit at constant
+// offsets from one address, a warp writes / reads 8 x 256 (128) contiguous bytes of one 2048 (1024)-byte tile.
+// EIGHT values per block: the xy-xy part of every off-diagonal block of this problem is symmetric (H_ab = X0^T S Y0 has
+// -(alpha I + c1 f f^T) there, and so has its transpose), so m10 is not stored:
+//   plane 0..7 = m00, m01 (= m10), m02, m11, m12, m20, m21, m22.
+// 64 instead of 72 bytes per block in k_linearize's store stream and in the SpMV's read stream.
+constexpr int kBlockVals = 8;
+__device__ __forceinline__ int64_t block_base(int64_t slot) { return (slot >> 5) * (kBlockVals * 32) + (slot & 31); }
+__host__ __device__ constexpr int block_plane(int rc) { return rc < 3 ? rc : (rc == 3 ? 1 : rc - 1); }   // row-major (r, c) -> plane
 
 __device__ __forceinline__ void ld_rec(HalfEdgeRec& r, const HalfEdgeRec* p, uint64_t pol) {
   uint64_t w;
@@ -164,12 +170,11 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, const HalfEdgeRec* __r
         st_stream(out + 0 * 32, -T.U00, pol.stream);
         st_stream(out + 1 * 32, -T.U01, pol.stream);
         st_stream(out + 2 * 32, -T.sc0, pol.stream);
-        st_stream(out + 3 * 32, -T.U01, pol.stream);
-        st_stream(out + 4 * 32, -T.U11, pol.stream);
-        st_stream(out + 5 * 32, -T.sc1, pol.stream);
-        st_stream(out + 6 * 32, T.e0, pol.stream);
-        st_stream(out + 7 * 32, T.e1, pol.stream);
-        st_stream(out + 8 * 32, T.o22, pol.stream);
+        st_stream(out + 3 * 32, -T.U11, pol.stream);
+        st_stream(out + 4 * 32, -T.sc1, pol.stream);
+        st_stream(out + 5 * 32, T.e0, pol.stream);
+        st_stream(out + 6 * 32, T.e1, pol.stream);
+        st_stream(out + 7 * 32, T.o22, pol.stream);
       }
     }
     orun += __popc(om);
@@ -381,23 +386,21 @@ k_expand(const int32_t* __restrict__ block_src, const uint32_t* __restrict__ col
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nslots) return;
   const int32_t s = block_src[i];
-  double v[9];
+  double v[kBlockVals];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) v[c] = 0.0;
+  for (int c = 0; c < kBlockVals; ++c) v[c] = 0.0;
   if (s >= 0) {
     const double* in = Hup + block_base(s);
 #pragma unroll
-    for (int c = 0; c < 9; ++c) v[c] = in[c * 32];
+    for (int c = 0; c < kBlockVals; ++c) v[c] = in[c * 32];
   }
   T* out = Hoff + block_base(i);
   if (!(cols[i] & kFlagSideB)) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) out[c * 32] = (T)v[c];
-  } else {
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) out[(3 * r + c) * 32] = (T)v[3 * c + r];
+    for (int c = 0; c < kBlockVals; ++c) out[c * 32] = (T)v[c];
+  } else {      // transpose: (m00, m01, m02, m11, m12, m20, m21, m22) -> (m00, m01, m20, m11, m21, m02, m12, m22)
+    out[0 * 32] = (T)v[0]; out[1 * 32] = (T)v[1]; out[2 * 32] = (T)v[5]; out[3 * 32] = (T)v[3];
+    out[4 * 32] = (T)v[6]; out[5 * 32] = (T)v[2]; out[6 * 32] = (T)v[4]; out[7 * 32] = (T)v[7];
   }
 }
 
@@ -600,36 +603,36 @@ k_spmv(const double4* __restrict__ p4, RowLayout L, const uint32_t* __restrict__
       y2 = fma(a02, p.x, fma(a12, p.y, a22 * p.z));
     }
     const uint32_t* cp = cols + tile0 * kSlice + lane;       // round k: + 32 k
-    const T* hp = Hoff + tile0 * 288 + lane;                 // round k: + 288 k, value c: + 32 c
+    const T* hp = Hoff + tile0 * (kBlockVals * 32) + lane;   // round k: + 256 k, value c: + 32 c
     constexpr int U = 4;     // rounds in flight per thread: 4 x (9 block words + column + gathered p) loads
     int k = kPass == kSpmvHalo ? (int)info.w : 0;
     for (; k + U <= deg; k += U) {
-      uint32_t j[U]; double h[U][9]; double4 pj[U];
+      uint32_t j[U]; double h[U][kBlockVals]; double4 pj[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) j[u] = ld_stream_u32(cp + (int64_t)(k + u) * kSlice, pol.stream) & kIdxMask;
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int c = 0; c < 9; ++c) h[u][c] = ld_blockval(hp + (int64_t)(k + u) * 288 + c * 32, pol.stream);
+        for (int c = 0; c < kBlockVals; ++c) h[u][c] = ld_blockval(hp + (int64_t)(k + u) * (kBlockVals * 32) + c * 32, pol.stream);
 #pragma unroll
       for (int u = 0; u < U; ++u) { DCS_ASSERT((int32_t)j[u] < n_loc); pj[u] = ld_keep4(p4 + j[u], pol.keep); }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         y0 = fma(h[u][0], pj[u].x, fma(h[u][1], pj[u].y, fma(h[u][2], pj[u].z, y0)));
-        y1 = fma(h[u][3], pj[u].x, fma(h[u][4], pj[u].y, fma(h[u][5], pj[u].z, y1)));
-        y2 = fma(h[u][6], pj[u].x, fma(h[u][7], pj[u].y, fma(h[u][8], pj[u].z, y2)));
+        y1 = fma(h[u][1], pj[u].x, fma(h[u][3], pj[u].y, fma(h[u][4], pj[u].z, y1)));
+        y2 = fma(h[u][5], pj[u].x, fma(h[u][6], pj[u].y, fma(h[u][7], pj[u].z, y2)));
       }
     }
     for (; k < deg; ++k) {
       const uint32_t j = ld_stream_u32(cp + (int64_t)k * kSlice, pol.stream) & kIdxMask;
-      double h[9];
+      double h[kBlockVals];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) h[c] = ld_blockval(hp + (int64_t)k * 288 + c * 32, pol.stream);
+      for (int c = 0; c < kBlockVals; ++c) h[c] = ld_blockval(hp + (int64_t)k * (kBlockVals * 32) + c * 32, pol.stream);
       DCS_ASSERT((int32_t)j < n_loc);
       const double4 pj = ld_keep4(p4 + j, pol.keep);
       y0 = fma(h[0], pj.x, fma(h[1], pj.y, fma(h[2], pj.z, y0)));
-      y1 = fma(h[3], pj.x, fma(h[4], pj.y, fma(h[5], pj.z, y1)));
-      y2 = fma(h[6], pj.x, fma(h[7], pj.y, fma(h[8], pj.z, y2)));
+      y1 = fma(h[1], pj.x, fma(h[3], pj.y, fma(h[4], pj.z, y1)));
+      y2 = fma(h[5], pj.x, fma(h[6], pj.y, fma(h[7], pj.z, y2)));
     }
     q[0 * L.ldn + lr] = y0; q[1 * L.ldn + lr] = y1; q[2 * L.ldn + lr] = y2;
     dot = fma(p.x, y0, fma(p.y, y1, p.z * y2));
@@ -769,7 +772,7 @@ k_chain_factor(const double* __restrict__ Adiag, const T* __restrict__ Hoff, con
       for (int32_t d = 0; d < cc; ++d) {
         const int64_t sl = slot[ci + d];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) E[c] += (double)Hoff[block_base(sl) + c * 32];
+        for (int c = 0; c < 9; ++c) E[c] += (double)Hoff[block_base(sl) + block_plane(c) * 32];
       }
       // L = E^T Sinv   (Sinv symmetric)
       const double S[9] = {s00, s01, s02, s01, s11, s12, s02, s12, s22};

@@ -131,8 +131,8 @@ k_linearize_sc(const double4* __restrict__ xyt, RowLayout L, const HalfEdgeRec* 
         DCS_ASSERT(idx >= 0 && idx < L.ldu);
         double* out = Hup + block_base(idx);
         out[0 * 32] = -T.U00; out[1 * 32] = -T.U01; out[2 * 32] = -T.sc0;
-        out[3 * 32] = -T.U01; out[4 * 32] = -T.U11; out[5 * 32] = -T.sc1;
-        out[6 * 32] = T.e0;   out[7 * 32] = T.e1;   out[8 * 32] = T.o22;
+        out[3 * 32] = -T.U11; out[4 * 32] = -T.sc1;
+        out[5 * 32] = T.e0;   out[6 * 32] = T.e1;   out[7 * 32] = T.o22;
       }
     }
     orun += __popc(om);
