@@ -180,6 +180,8 @@ DCS_API void dcs_destroy(dcs_handle* h);
  * Any output pointer may be NULL.  Shapes: residuals E x 3, jacobians E x 18
  * (row-major 3x6 per edge: d e / d(pa, pb), after DCS and the Huber corrector),
  * psi E, rho1 E (Huber rho'), gradient N x 3 (zeros at the fixed pose). */
+/* Single-rank METHOD 0/1 handles for the per-edge outputs (cost and gradient work everywhere; with switchable_on the
+ * cost includes the switch priors and the gradient is the pose part at the current switches). */
 DCS_API int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost,
                  double* residuals, double* jacobians, double* psi, double* rho1,
                  double* gradient);

@@ -345,6 +345,13 @@ def test_method2_rejects_what_it_does_not_support():
     with D.Solver(g, dcs_on=True) as s:
         with pytest.raises(D.DcsError):
             s.switches()
+    with D.Solver(g, dcs_on=False, switchable_on=1) as s:
+        with pytest.raises(D.DcsError):
+            s.evaluate()                                         # the per-edge dump is the METHOD 0/1 functors
+        ev = s.evaluate(residuals=False, jacobians=False)       # cost + gradient: every switch is 1 -> METHOD 0's
+        ref = O.Oracle(g, dcs_on=False).evaluate()
+        assert abs(ev["cost"] - ref["cost"]) <= 1e-12 * ref["cost"]
+        assert np.abs(ev["gradient"] - ref["gradient"]).max() <= 1e-11 * np.abs(ref["gradient"]).max()
 
 
 def test_batched_tiny_solves_match_separate_solves_and_the_oracle():

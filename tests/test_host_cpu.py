@@ -297,3 +297,23 @@ def test_main_cli_usage_and_method_guard():
     exe = os.path.join(ROOT, "toy-robust-backend-slam_b200", "host", "main")
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 255 and p.stdout.startswith("Usage: ")          # reference main.cpp:35-40 returns -1
+
+
+def test_bench_trace_comparison_gates():
+    """bench.py's N-rank vs 1-rank gate: leading iterations to 1e-9, count of agreeing iterations, worst deviation."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    mk = lambda c, ok: types.SimpleNamespace(cost=c, step_is_successful=ok)
+    ref = [mk(10.0 / (i + 1), 1) for i in range(20)]
+    same = [mk(t.cost * (1 + 1e-12), 1) for t in ref]
+    ok, rel, k, agree, rel_all = bench.compare_traces(same, ref, 11)
+    assert ok and k == 11 and agree == 20 and rel < 1e-11 and rel_all < 1e-11
+    drift = [mk(t.cost * (1 + (1e-12 if i < 15 else 1e-6)), 1) for i, t in enumerate(ref)]
+    ok, rel, k, agree, rel_all = bench.compare_traces(drift, ref, 11)
+    assert ok and agree == 15 and 0.9e-6 < rel_all < 1.1e-6
+    flip = [mk(t.cost, 0 if i == 5 else 1) for i, t in enumerate(ref)]
+    ok, rel, k, agree, rel_all = bench.compare_traces(flip, ref, 11)
+    assert not ok and agree == 5

@@ -505,15 +505,29 @@ int build_halo(dcs_handle* h, int32_t nh) {
   h->halo_cnt_all = all;
   const int32_t ns = h->halo_send_off[W];
   CK(h->halo_send_idx.alloc((size_t)std::max(ns, 1)));
-  // swap the index lists: I send each owner the (global) indices I need from it; I receive what each peer needs from me
-  CKN(nccl_api().GroupStart());
-  for (int r = 0; r < W; ++r) {
-    if (r == h->rank) continue;
-    const int32_t cr = h->halo_recv_off[r + 1] - h->halo_recv_off[r], cs = h->halo_send_off[r + 1] - h->halo_send_off[r];
-    if (cr > 0) CKN(nccl_api().Send(h->halo_recv_idx.p + h->halo_recv_off[r], (size_t)cr, ncclInt32, r, h->comm, st));
-    if (cs > 0) CKN(nccl_api().Recv(h->halo_send_idx.p + h->halo_send_off[r], (size_t)cs, ncclInt32, r, h->comm, st));
+  // Swap the index lists with ONE all-gather of every rank's receive list (global ids, grouped by owner, padded to the
+  // longest list): what rank r needs from me is a contiguous slice of r's list.  (A grouped ncclSend/ncclRecv to every
+  // peer would make NCCL set up a point-to-point connection per peer pair here: seconds at create time.)
+  {
+    int32_t max_nr = 1;
+    for (int r = 0; r < W; ++r) {
+      int32_t t = 0;
+      for (int q = 0; q < W; ++q) t += all[(size_t)r * W + q];
+      max_nr = std::max(max_nr, t);
+    }
+    DevBuf<int32_t> lists;
+    CK(lists.alloc((size_t)W * max_nr));
+    if (nr > 0) CK(cudaMemcpyAsync(lists.p + (size_t)h->rank * max_nr, h->halo_recv_idx.p, (size_t)nr * 4, cudaMemcpyDeviceToDevice, st));
+    CKN(nccl_api().AllGather(lists.p + (size_t)h->rank * max_nr, lists.p, (size_t)max_nr, ncclInt32, h->comm, st));
+    for (int r = 0; r < W; ++r) {
+      if (r == h->rank) continue;
+      const int32_t cs = h->halo_send_off[r + 1] - h->halo_send_off[r];
+      int32_t off = 0;      // rank r's list is grouped by owner: my slice starts after the owners below me
+      for (int q = 0; q < h->rank; ++q) off += all[(size_t)r * W + q];
+      if (cs > 0) CK(cudaMemcpyAsync(h->halo_send_idx.p + h->halo_send_off[r], lists.p + (size_t)r * max_nr + off, (size_t)cs * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));     // `lists` is freed here
   }
-  CKN(nccl_api().GroupEnd());
   CK(h->halo_send_buf.alloc((size_t)std::max(ns, 1)));
   if (ns > 0) LAUNCH(k_global_to_own, cdiv(ns, 256), 256, st, h->halo_send_idx.p, ns, h->row_lo, h->rank_of.p);   // peers asked with global ids
   CK(cudaStreamSynchronize(st));
@@ -1077,6 +1091,10 @@ int dcs_evaluate(dcs_handle* h, const double* pose_xyt, double* cost, double* re
   CKS(read_scalars(h));
   if (cost) *cost = h->h_scal[S_COST];
   const int32_t E = h->E;
+  if ((residuals || jacobians || psi || rho1) && h->sc) {
+    g_err = "dcs_evaluate: the per-edge dump evaluates the METHOD 0/1 functors; not available on switchable_on handles";
+    return DCS_ERR_ARG;
+  }
   if ((residuals || jacobians || psi || rho1) && h->world > 1) {
     g_err = "dcs_evaluate: per-edge outputs are available on single-rank handles only";
     return DCS_ERR_ARG;

@@ -326,7 +326,9 @@ class Solver:
         cost = C.c_double()
         r = np.empty((E, 3)) if residuals else None
         J = np.empty((E, 3, 6)) if jacobians else None
-        psi = np.empty(E); rho1 = np.empty(E)
+        per_edge = residuals or jacobians
+        psi = np.empty(E) if per_edge else None
+        rho1 = np.empty(E) if per_edge else None
         g = np.empty((N, 3)) if gradient else None
         self._ck(self.lib.dcs_evaluate(self.h, _ptr(x), C.byref(cost), _ptr(r), _ptr(J), _ptr(psi), _ptr(rho1), _ptr(g)),
                  "dcs_evaluate")
