@@ -510,7 +510,7 @@ meas = rng.normal(0, 1, (len(ea), 3))
 g = D.Graph(pose, ea, eb, meas, kind)
 for opts in (dict(dcs_on=True), dict(dcs_on=False), dict(dcs_on=False, switchable_on=1), dict(dcs_on=True, preconditioner=0)):
     with D.Solver(g, max_num_iterations=3, pcg_max_iter=256, **opts) as s:
-        s.evaluate(); s.hessian(); s.cost(); x, sm, tr = s.solve()
+        s.evaluate(residuals=not opts.get("switchable_on"), jacobians=not opts.get("switchable_on")); s.hessian(); s.cost(); x, sm, tr = s.solve()
         print("check", opts, sm.final_cost)
 g0 = D.Graph(np.zeros((3, 3)), [], [], np.zeros((0, 3)), [])
 with D.Solver(g0) as s:

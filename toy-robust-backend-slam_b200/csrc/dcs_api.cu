@@ -682,10 +682,10 @@ int spmv_product(dcs_handle* h, const double* D, int out_slot, int rotate_rz) {
 int pcg_iteration(dcs_handle* h, const double* D) {
   CKS(spmv_product(h, D, S_PQ, 1));
   if (h->opt.preconditioner == 1) {
-    LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
-           h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    k_pcg_chain<false><<<h->ntiles, kChainThreads, kChainSmemBytes, h->stream>>>((const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
+        h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
-    ++g_launches; ++t_launches;
+    g_launches += 2; t_launches += 2;
   } else {
     LAUNCH(k_pcg_update, h->vec_grid(), kVecThreads, h->stream, h->p4.p, h->q.p, h->Minv.p, 0, h->nrows, h->ldn, h->w.p,
            h->r.p, h->z.p, h->partials.p, h->tickets.p + 4, h->scal.p);
@@ -705,8 +705,9 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_chain_factor<double>, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->rank_of.p, h->nrows, h->ldn,
            h->ldh, h->chL.p, h->chS.p);
-    LAUNCH(k_pcg_chain<true>, h->ntiles, 32, h->stream, rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->perm.p, 0, h->nrows,
-           h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    k_pcg_chain<true><<<h->ntiles, kChainThreads, kChainSmemBytes, h->stream>>>(rhs, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p, h->perm.p, 0, h->nrows,
+        h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    ++g_launches; ++t_launches;
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     ++g_launches; ++t_launches;
   } else
@@ -882,6 +883,11 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(cudaSetDevice(o->device));
   int sm_count_ = 148;
   cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, o->device);
+  CK(cudaFuncSetAttribute(k_pcg_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+  CK(cudaFuncSetAttribute(k_pcg_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+  // two 85-KB tiles per SM: ask for the largest shared-memory carve-out (the default heuristic sizes it for one CTA)
+  CK(cudaFuncSetAttribute(k_pcg_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_pcg_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
   const double t_c0 = now_s();
   auto lap = [&](const char* what) { if (std::getenv("DCS_CREATE_TIMING")) { cudaDeviceSynchronize(); std::fprintf(stderr, "[dcs_create] %-28s %.3f s\n", what, now_s() - t_c0); } };

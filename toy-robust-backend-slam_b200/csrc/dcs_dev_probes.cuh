@@ -107,8 +107,8 @@ DCS_API int dcs_debug_pcg_stages(dcs_handle* h, int repeats, double* out6) {
     cudaEventRecord(ev[1], h->stream);
     CKS(allreduce_sum(h, h->scal.p + S_PQ, 1));
     cudaEventRecord(ev[2], h->stream);
-    LAUNCH(k_pcg_chain<false>, h->ntiles, 32, h->stream, (const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
-           h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
+    k_pcg_chain<false><<<h->ntiles, kChainThreads, kChainSmemBytes, h->stream>>>((const double*)nullptr, h->is_free.p, h->p4.p, h->q.p, h->chL.p, h->chS.p,
+        h->perm.p, 0, h->nrows, h->ldn, h->w.p, h->r.p, h->z.p, h->p4.p, h->task_part.p, h->scal.p);
     k_fold_tasks<2, 0><<<fold_blocks(h->ntiles), kFoldThreads, 0, h->stream>>>(h->task_part.p, h->ntiles, h->scal.p + S_TMP, h->scal.p, 0, h->fold_ws.p, h->tickets.p + 6);
     cudaEventRecord(ev[3], h->stream);
     CKS(allreduce_sum(h, h->scal.p + S_TMP, 2));
