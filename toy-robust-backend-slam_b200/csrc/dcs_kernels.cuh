@@ -884,31 +884,78 @@ k_pcg_chain(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free,
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // phase 2 (warp 0, lane = segment): forward substitution y_j = r_j - L_j y_{j-1}, then z_j = S_j^-1 y_j - L_{j+1}^T z_{j+1}
+  // phase 2 (warp 0, lane = segment): forward substitution y_j = r_j - L_j y_{j-1}, then z_j = S_j^-1 y_j - L_{j+1}^T z_{j+1}.
+  // The dependent chain of a step is four fp64 operations; everything else of step j + 1 (shared-memory loads, float ->
+  // double conversions) is issued BEFORE the stores of step j, by hand: the compiler keeps loads behind stores into the
+  // same dynamic shared array, which put ~100 cycles of load + convert latency on the critical path of every step.
   if (wid == 0) {
     double y0 = 0, y1 = 0, y2 = 0;
+    double ln[9], rn[3];
+    {
+      const int k = lane * 33, f = lane;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) ln[c] = (double)s_L[c][f];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rn[c] = s_v[c][k];
+    }
 #pragma unroll 4
     for (int j = 0; j < kChainSeg; ++j) {
-      const int k = lane * 33 + j, f = j * 32 + lane;
-      const double n0 = s_v[0][k] - (s_L[0][f] * y0 + s_L[1][f] * y1 + s_L[2][f] * y2);
-      const double n1 = s_v[1][k] - (s_L[3][f] * y0 + s_L[4][f] * y1 + s_L[5][f] * y2);
-      const double n2 = s_v[2][k] - (s_L[6][f] * y0 + s_L[7][f] * y1 + s_L[8][f] * y2);
+      const int k = lane * 33 + j;
+      double lc[9], rc[3];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) lc[c] = ln[c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rc[c] = rn[c];
+      if (j + 1 < kChainSeg) {
+        const int f1 = (j + 1) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) ln[c] = (double)s_L[c][f1];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rn[c] = s_v[c][k + 1];
+      }
+      // dependent depth 3: (r - l0 y0 - l2 y2) - l1 y1, the product l1 y1 beside the first fma
+      const double n0 = fma(-lc[2], y2, fma(-lc[0], y0, rc[0])) - lc[1] * y1;
+      const double n1 = fma(-lc[5], y2, fma(-lc[3], y0, rc[1])) - lc[4] * y1;
+      const double n2 = fma(-lc[8], y2, fma(-lc[6], y0, rc[2])) - lc[7] * y1;
       y0 = n0; y1 = n1; y2 = n2;
       s_v[0][k] = y0; s_v[1][k] = y1; s_v[2][k] = y2;
     }
     double z0 = 0, z1 = 0, z2 = 0;
+    double an[6], vn[3];       // S_j^-1 and y_j of the step to come; its L_{j+1} is the forward factor of the step just done
+    {
+      const int j = kChainSeg - 1, k = lane * 33 + j, f = j * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) an[c] = (double)s_S[c][f];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vn[c] = s_v[c][k];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) ln[c] = 0.0;       // no step after the last
+    }
 #pragma unroll 4
     for (int j = kChainSeg - 1; j >= 0; --j) {
-      const int k = lane * 33 + j, f = j * 32 + lane, fn = f + 32;
-      const bool has_next = j + 1 < kChainSeg;
-      float l[9];
+      const int k = lane * 33 + j, f = j * 32 + lane;
+      double ac[6], vc[3], lc[9];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) l[c] = has_next ? s_L[c][fn] : 0.0f;
-      const double a0 = s_S[0][f], a1 = s_S[1][f], a2 = s_S[2][f], a3 = s_S[3][f], a4 = s_S[4][f], a5 = s_S[5][f];
-      const double v0 = s_v[0][k], v1 = s_v[1][k], v2 = s_v[2][k];
-      const double n0 = a0 * v0 + a1 * v1 + a2 * v2 - (l[0] * z0 + l[3] * z1 + l[6] * z2);
-      const double n1 = a1 * v0 + a3 * v1 + a4 * v2 - (l[1] * z0 + l[4] * z1 + l[7] * z2);
-      const double n2 = a2 * v0 + a4 * v1 + a5 * v2 - (l[2] * z0 + l[5] * z1 + l[8] * z2);
+      for (int c = 0; c < 6; ++c) ac[c] = an[c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vc[c] = vn[c];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) lc[c] = ln[c];
+      if (j > 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) an[c] = (double)s_S[c][f - 32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vn[c] = s_v[c][k - 1];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) ln[c] = (double)s_L[c][f];     // L_j: what step j - 1 needs
+      }
+      // S^-1 y does not depend on z: off the chain; then depth 3 as above
+      const double b0 = ac[0] * vc[0] + ac[1] * vc[1] + ac[2] * vc[2];
+      const double b1 = ac[1] * vc[0] + ac[3] * vc[1] + ac[4] * vc[2];
+      const double b2 = ac[2] * vc[0] + ac[4] * vc[1] + ac[5] * vc[2];
+      const double n0 = fma(-lc[6], z2, fma(-lc[0], z0, b0)) - lc[3] * z1;
+      const double n1 = fma(-lc[7], z2, fma(-lc[1], z0, b1)) - lc[4] * z1;
+      const double n2 = fma(-lc[8], z2, fma(-lc[2], z0, b2)) - lc[5] * z1;
       z0 = n0; z1 = n1; z2 = n2;
       s_v[0][k] = z0; s_v[1][k] = z1; s_v[2][k] = z2;
     }
