@@ -427,3 +427,22 @@ def test_lm_matches_dense_restatement(dcs):
     assert [t.step_is_successful for t in tr[1:]] == flags
     assert np.allclose([t.cost for t in tr], costs, rtol=1e-9, atol=1e-14)
     assert sum(flags) >= 5
+
+
+@pytest.mark.parametrize("fixture,seed", [("SYN10K_1000_s777", 777), ("SYN10K_1000", 12345)])
+def test_syn10k_fixtures_are_the_generator_and_the_oracle(fixture, seed):
+    """The 10 000-pose fixtures of the full-solve GPU test (tests/golden/make_golden.py syn10k): the committed graph is what
+    the C++ generator + injector produce for that seed, the committed initial cost is the oracle's, and (one fixture, one
+    iteration: the factorisation has 6.6 M non-zeros) the first LM step of the committed trace is reproduced."""
+    import dcs_b200 as D
+    z = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    g = D.Graph.synthetic(10000, 10688, n_bogus=1000, bogus_seed=seed)
+    for k in ("pose_xyt", "edge_a", "edge_b", "meas_xyt", "kind"):
+        assert np.array_equal(getattr(g, k), z[k]), k
+    ora = O.Oracle(g, dcs_on=True, num_threads=os.cpu_count() or 1)
+    assert np.isclose(ora.evaluate()["cost"], z["trace_cost_dcs1"][0], rtol=1e-13)
+    if seed == 777:
+        x, s, tr = ora.solve(max_num_iterations=1)
+        assert np.allclose([t.cost for t in tr], z["trace_cost_dcs1"][:2], rtol=1e-12)
+        assert tr[1].step_is_successful == z["trace_ok_dcs1"][1]
+        assert int(s.factor_nnz) == int(z["factor_nnz"])

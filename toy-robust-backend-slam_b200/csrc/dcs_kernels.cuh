@@ -103,9 +103,6 @@ __device__ __forceinline__ void ld_pose(PoseRec& r, const double4* p, uint64_t p
 #ifndef DCS_K1_PF_OWN
 #define DCS_K1_PF_OWN 1
 #endif
-#ifndef DCS_K1_PF_AHEAD
-#define DCS_K1_PF_AHEAD 0
-#endif
 struct K1Stage { HalfEdgeRec rec[kK1Rounds]; PoseRec pose[kK1Rounds]; };
 
 __global__ void __launch_bounds__(kRowsPerBlock, DCS_K1_WARPS)
@@ -128,25 +125,12 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, const HalfEdgeRec* __r
   int orun = ti.y;                                  // compact index of the task's next owner block
   // Bulk L2 prefetches (one instruction by one lane, no destination register, no scoreboard):
   //  * DCS_K1_PF_OWN: the task's own record run is ONE contiguous range (kmax KB) - start its DRAM fetch now so the
-  //    pipeline's record loads find their lines in L2;
-  //  * DCS_K1_PF_AHEAD = G > 0: everything task + G will read at its start-up and stream afterwards (its row infos,
-  //    own poses and record run are contiguous ranges too).  G ~ the number of resident tasks, i.e. the task that
-  //    starts when this one ends: every task then starts from L2 instead of paying two DRAM latencies in series.
+  //    pipeline's record loads find their lines in L2.  (Prefetching a whole task ahead - the row infos, own poses and
+  //    record run of the task that starts when this one ends - was measured and changed nothing.)
   constexpr int kPrefetchTiles = 32;
 #if DCS_K1_PF_OWN
   if (lane == 0 && kmax > kR)
     prefetch_l2_bulk(recs + ((int64_t)ti.x + kR) * kSlice, (uint32_t)(min(kmax - kR, kPrefetchTiles) * kSlice * (int)sizeof(HalfEdgeRec)));
-#endif
-#if DCS_K1_PF_AHEAD > 0
-  const int tf = task + DCS_K1_PF_AHEAD;
-  int2 tif = make_int2(0, 0), tif1 = make_int2(0, 0);
-  if (tf < L.ntasks) {                              // warp-uniform
-    tif = L.task_info[tf]; tif1 = L.task_info[tf + 1];
-    if (lane == 0) {
-      prefetch_l2_bulk(L.rowinfo + (int64_t)tf * kSlice, kSlice * (int)sizeof(uint4));
-      prefetch_l2_bulk(xyt + (int64_t)tf * kSlice, kSlice * (int)sizeof(double4));
-    }
-  }
 #endif
   double d00 = 0, d01 = 0, d02 = 0, d11 = 0, d12 = 0, d22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
 
@@ -221,10 +205,6 @@ k_linearize(const double4* __restrict__ xyt, RowLayout L, const HalfEdgeRec* __r
       for (int u = 0; u < kR; ++u) process(B.rec[u], B.pose[u], k + kR + u < deg);
     }
   }
-#if DCS_K1_PF_AHEAD > 0
-  if (lane == 0 && tf < L.ntasks && tif1.x > tif.x)     // the future task's record run (first kPrefetchTiles tiles)
-    prefetch_l2_bulk(recs + (int64_t)tif.x * kSlice, (uint32_t)(min(tif1.x - tif.x, kPrefetchTiles) * kSlice * (int)sizeof(HalfEdgeRec)));
-#endif
   if (lr < L.nrows) {
     Hdiag[0 * L.ldn + lr] = d00; Hdiag[1 * L.ldn + lr] = d01; Hdiag[2 * L.ldn + lr] = d02;
     Hdiag[3 * L.ldn + lr] = d11; Hdiag[4 * L.ldn + lr] = d12; Hdiag[5 * L.ldn + lr] = d22;
