@@ -319,7 +319,13 @@ k_xchg_sum(XchgPeers X, double* vals, int count) {
     for (int k = 0; k < count; ++k) dst->data[e & 1][X.rank][k] = vals[k];
     __threadfence_system();
     st_release_sys(&dst->flag[X.rank], e);
-    while (ld_acquire_sys(&mine->flag[t]) < e) { }
+    // a peer that never arrives (its process died, or the ranks issued different call sequences) must not hang the
+    // device for good: after ~2 minutes of polling (ranks may enter a collective call seconds apart; NCCL would wait
+    // too) the kernel traps, which surfaces as DCS_ERR_CUDA on the host
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flag[t]) < e) {
+      if (clock64() - t0 > 240000000000LL) __trap();
+    }
     for (int k = 0; k < count; ++k) s_v[t][k] = __ldcg(&mine->data[e & 1][t][k]);
   }
   __syncwarp();
