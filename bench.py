@@ -432,7 +432,7 @@ def main():
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "n_poses": n_poses, "n_edges": g.n_edges, "partition": f"pose-range x{world}",
-                   "l2": "inputs larger than L2 (0.26 GB half-edge record stream read + 0.38 GB of blocks, diagonals and gradient written per launch)",
+                   "l2": "inputs larger than L2 (0.26 GB half-edge record stream + 0.03 GB of poses read, 0.33 GB of blocks, diagonals and gradient written per launch)",
                    "step": "k_linearize + k_fold_tasks; output = the reference's structure (one 3x3 block per edge, diagonal blocks, "
                            "gradient).  The expansion into the SpMV's row storage (k_expand, once per LM iteration) is NOT in "
                            "`value`; `ms_per_step_with_solver_setup` includes it",
