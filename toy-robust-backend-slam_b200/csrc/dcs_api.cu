@@ -21,6 +21,7 @@
 #include "dcs_kernels.cuh"
 #include "dcs_nccl.h"
 #include "dcs_pattern.cuh"
+#include "dcs_pcg_cluster.cuh"
 #include "dcs_switchable.cuh"
 
 using namespace dcs;
@@ -267,6 +268,8 @@ struct dcs_handle {
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
   cudaGraphExec_t pcg_graph = nullptr;
+  bool cluster_pcg = false;                // small single-rank graph with the chain preconditioner: k_pcg_cluster runs the whole solve
+  int32_t cluster_cols_words = 0;          // column words k_pcg_cluster may stage in shared memory (0: read them from global memory)
   int pcg_graph_iters = 0;
   const double* pcg_graph_D = nullptr;
   bool have_lin = false;
@@ -702,6 +705,35 @@ int pcg_solve(dcs_handle* h, double inv_radius, const double* lambda_explicit, c
   CKS(ensure_mirror(h));
   LAUNCH(k_precond, h->vec_grid(), 256, h->stream, h->Hdiag.p, h->lmdiag.p, h->scale.p, h->is_free.p, h->nrows, h->ldn, inv_radius,
          lambda_explicit, h->Adiag.p, h->Minv.p);
+  if (h->cluster_pcg) {     // small graph: factorise, then ONE cluster launch runs the solve to convergence
+    LAUNCH(k_chain_factor<double>, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->rank_of.p, h->nrows, h->ldn,
+           h->ldh, h->chL.p, h->chS.p);
+    const int batch = std::max(1, h->opt.pcg_check_every);
+    const int max_iter = cdiv(std::max(1, h->opt.pcg_max_iter), batch) * batch;     // whole batches, like the graph replays below
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)h->ntiles); cfg.blockDim = dim3(kClThreads);
+    cfg.dynamicSmemBytes = kClSmemBase + (size_t)h->cluster_cols_words * 4; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)h->ntiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_pcg_cluster, rhs, (const uint8_t*)h->is_free.p, h->layout(), (const uint32_t*)h->cols.p, (const double*)h->Hoff.p,
+                          (const double*)h->Adiag.p, (const float*)h->chL.p, (const float*)h->chS.p, (const uint16_t*)h->perm.p, h->n_loc,
+                          h->cluster_cols_words, (int32_t)batch, (int32_t)max_iter, h->opt.pcg_rel_tol, h->p4.p, h->w.p, h->scal.p));
+    ++g_launches; ++t_launches;
+    CKS(read_scalars(h));
+    const double rr0 = h->h_scal[S_RR0], rr = h->h_scal[S_RR];
+    const int iters = (int)h->h_scal[S_PCG_ITERS];
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->pcg_ms += ms;
+    h->pcg_iters_total += iters;
+    if (iters_out) *iters_out = iters;
+    if (relres_out) *relres_out = (rr0 > 0.0) ? std::sqrt(rr / rr0) : 0.0;
+    return DCS_OK;
+  }
   if (h->opt.preconditioner == 1) {
     LAUNCH(k_chain_factor<double>, h->ntiles, 32, h->stream, h->Adiag.p, h->Hoff.p, h->slot.p, h->chain_idx.p, h->chain_cnt.p, h->rank_of.p, h->nrows, h->ldn,
            h->ldh, h->chL.p, h->chS.p);
@@ -887,6 +919,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(cudaFuncSetAttribute(k_pcg_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
   // two 85-KB tiles per SM: ask for the largest shared-memory carve-out (the default heuristic sizes it for one CTA)
   CK(cudaFuncSetAttribute(k_pcg_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClSmemMax));
   CK(cudaFuncSetAttribute(k_pcg_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
   const double t_c0 = now_s();
@@ -1060,6 +1093,24 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   CK(h->tickets.alloc_zero(8, st));
   CK(h->fold_ws.alloc_zero(4 * kFoldMaxBlocks, st));
   h->ntiles = (int)(h->ldn / kChainTile);
+  {   // small single-rank graphs: the whole PCG solve in one cluster launch (dcs_pcg_cluster.cuh).  DCS_PCG_CLUSTER=0 keeps
+      // the general path (CUDA-graph batches of five kernels per iteration)
+    const char* ev = std::getenv("DCS_PCG_CLUSTER");
+    const bool want = !(ev && std::atoi(ev) == 0);
+    if (want && h->world == 1 && h->opt.preconditioner == 1 && h->ntiles >= 1 && h->ntiles <= kClMaxTiles) {
+      h->cluster_cols_words = (kClSmemBase + (size_t)h->ldh * 4 <= kClSmemMax) ? (int32_t)h->ldh : 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)h->ntiles); cfg.blockDim = dim3(kClThreads);
+      cfg.dynamicSmemBytes = kClSmemBase + (size_t)h->cluster_cols_words * 4;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)h->ntiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, k_pcg_cluster, &cfg) == cudaSuccess && n_clusters >= 1) h->cluster_pcg = true;
+      else (void)cudaGetLastError();       // a device that cannot co-schedule the cluster: general path
+    }
+  }
   CK(h->chL.alloc_zero(9 * LN, st)); CK(h->chS.alloc_zero(6 * LN, st));
   CK(h->chain_idx.alloc_zero(LN, st)); CK(h->chain_cnt.alloc_zero(LN, st));
   if (h->nrows > 0) LAUNCH(k_chain_entries, cdiv(h->nrows, 256), 256, st, h->keys.p, nh, h->row_lo, h->nrows, h->chain_idx.p, h->chain_cnt.p);

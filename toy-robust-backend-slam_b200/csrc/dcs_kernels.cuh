@@ -20,7 +20,7 @@ namespace dcs {
 
 // scalar slots in the device scalar block
 enum { S_COST = 0, S_GSQ = 1, S_GMAX = 2, S_PQ = 3, S_RZ = 4, S_RZ_NEXT = 5, S_RR = 6, S_RR0 = 7,
-       S_WG = 8, S_WHW = 9, S_STEP_SQ = 10, S_XSQ = 11, S_CAND_COST = 12, S_TMP = 13 /* 13, 14 */, S_TRES = 16,
+       S_WG = 8, S_WHW = 9, S_STEP_SQ = 10, S_XSQ = 11, S_CAND_COST = 12, S_TMP = 13 /* 13, 14 */, S_PCG_ITERS = 15 /* k_pcg_cluster: iterations run */, S_TRES = 16,
        S_SC = 17 /* 17..21: METHOD 2 step sums */, S_SC_COST = 22 /* 22: cost, 23: sum s^2 */, S_COUNT = 24 };
 
 // Sliced-ELL layout of the owned rows (SELL-32 with a 1024-row sorting window).  Rows are ranked by (degree,
