@@ -417,7 +417,30 @@ def main():
         batch["config"] = ("dcs_solve_batch: 64 variants of INTEL (1228 poses, odometry + 150-213 loop edges each), plain residual + "
                            "Huber, 2 LM iterations each (the layer managers' evaluate_cost shape), handle creation included")
         batch["final_cost_first"] = sums[0].final_cost
-        extras = {"method2": m2, "batched_tiny_solves": batch}
+        # the reference's own largest dataset (METHOD 1) through both linear-solver paths: the one-launch cluster PCG
+        # (k_pcg_cluster, what small graphs use) and the general path (DCS_PCG_CLUSTER=0: CUDA-graph batches of five kernels)
+        small = {"config": "M3500 + 100 outlier loops, DCS on, 50 LM iterations, pcg_rel_tol 1e-12"}
+        runs = {}
+        for label, env in (("cluster_pcg", None), ("general_pcg", "0")):
+            if env is not None:
+                os.environ["DCS_PCG_CLUSTER"] = env           # read by dcs_create
+            try:
+                with D.Solver(gm, dcs_on=True, device=local_rank, max_num_iterations=2) as s3:     # warm-up on its own handle
+                    s3.solve()
+                with D.Solver(gm, dcs_on=True, device=local_rank) as s3:
+                    t0 = time.perf_counter()
+                    _, sm3, tr3 = s3.solve()
+                    dt3 = time.perf_counter() - t0
+            finally:
+                os.environ.pop("DCS_PCG_CLUSTER", None)
+            runs[label] = (sm3, tr3)
+            small[label] = {"seconds": dt3, "lm_iters_per_sec": (len(tr3) - 1) / dt3, "pcg_iterations": int(sm3.total_pcg_iterations),
+                            "us_per_pcg_iteration": 1e6 * sm3.linear_solver_time_s / max(1, sm3.total_pcg_iterations),
+                            "final_cost": sm3.final_cost, "max_true_residual": max(i.linear_solver_true_residual for i in tr3)}
+        (sa, ta), (sb, tb) = runs["cluster_pcg"], runs["general_pcg"]
+        small["same_accept_sequence"] = len(ta) == len(tb) and all(x.step_is_successful == y.step_is_successful for x, y in zip(ta, tb))
+        small["final_cost_rel_diff"] = abs(sa.final_cost - sb.final_cost) / abs(sb.final_cost)
+        extras = {"method2": m2, "batched_tiny_solves": batch, "small_graph_pcg": small}
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu:

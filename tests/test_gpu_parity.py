@@ -240,6 +240,51 @@ def test_chain_preconditioner_cuts_iterations_and_keeps_the_trace():
     assert res[1][0] < 0.75 * res[0][0], (res[0][0], res[1][0])
 
 
+def _solver_with_pcg_path(g, cluster, **kw):
+    """dcs_create reads DCS_PCG_CLUSTER: 0 keeps the general PCG path (CUDA-graph batches) on small graphs too."""
+    os.environ["DCS_PCG_CLUSTER"] = "1" if cluster else "0"
+    try:
+        return D.Solver(g, **kw)
+    finally:
+        os.environ.pop("DCS_PCG_CLUSTER", None)
+
+
+@pytest.mark.parametrize("name,dcs", [("INTEL_50_seed1", 1), ("M3500_100_seed1", 1), ("INTEL_0_seed1", 0)])
+def test_cluster_pcg_matches_the_general_path(name, dcs):
+    """Small graphs run the whole PCG solve in one cluster launch (k_pcg_cluster).  Same linear solves as the general
+    path (k_spmv / k_pcg_chain / k_pcg_direction in CUDA-graph batches): same iteration counts (both stop at multiples
+    of pcg_check_every), same step, same LM trace; and the oracle's exact Cholesky agrees with both."""
+    g, z = load_case(name)
+    x = z["pose_perturbed"]
+    rng = np.random.default_rng(11)
+    rhs = rng.normal(0, 1, (g.n_poses, 3)); rhs[g.fixed_pose] = 0
+    lam = np.full((g.n_poses, 3), 1e-2)
+    res = {}
+    for cl in (1, 0):
+        with _solver_with_pcg_path(g, cl, dcs_on=bool(dcs), pcg_rel_tol=1e-13) as s:
+            s.linearize(x)
+            w, it, rel = s.pcg_solve(lam, rhs)
+            w2, it2, _ = s.pcg_solve(lam, rhs)
+            assert it == it2 and np.array_equal(w, w2)                  # bit-reproducible on either path
+            res[cl] = (w, it, rel)
+    (w1, it1, rel1), (w0, it0, rel0) = res[1], res[0]
+    assert rel1 <= 1e-12 and rel0 <= 1e-12 and it1 > 0
+    assert abs(it1 - it0) <= 32, (it1, it0)
+    wo = O.Oracle(g, dcs_on=bool(dcs)).linear_solve(lam, rhs, x)
+    assert np.linalg.norm(w1 - wo) <= 1e-9 * np.linalg.norm(wo) and np.linalg.norm(w0 - wo) <= 1e-9 * np.linalg.norm(wo)
+    assert np.linalg.norm(w1 - w0) <= 1e-10 * np.linalg.norm(wo)
+    assert (w1[g.fixed_pose] == 0).all()
+    tr = {}
+    for cl in (1, 0):
+        with _solver_with_pcg_path(g, cl, dcs_on=bool(dcs)) as s:
+            tr[cl] = s.solve()
+    (xa, sa, ta), (xb, sb, tb) = tr[1], tr[0]
+    assert len(ta) == len(tb) and [i.step_is_successful for i in ta] == [i.step_is_successful for i in tb]
+    assert max(abs(a.cost - b.cost) / abs(b.cost) for a, b in zip(ta, tb)) <= 1e-9
+    assert abs(sa.final_cost - sb.final_cost) <= 1e-10 * abs(sb.final_cost)
+    assert np.abs(xa - xb).max() <= 1e-6
+
+
 def test_solve_is_bit_reproducible():
     g, _ = load_case("INTEL_50_seed1")
     with D.Solver(g, dcs_on=True, max_num_iterations=8) as s:

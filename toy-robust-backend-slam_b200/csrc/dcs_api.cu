@@ -1098,7 +1098,7 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     const char* ev = std::getenv("DCS_PCG_CLUSTER");
     const bool want = !(ev && std::atoi(ev) == 0);
     if (want && h->world == 1 && h->opt.preconditioner == 1 && h->ntiles >= 1 && h->ntiles <= kClMaxTiles) {
-      h->cluster_cols_words = (kClSmemBase + (size_t)h->ldh * 4 <= kClSmemMax) ? (int32_t)h->ldh : 0;
+      h->cluster_cols_words = h->ldh <= (int64_t)kClMaxColWords ? (int32_t)h->ldh : 0;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)h->ntiles); cfg.blockDim = dim3(kClThreads);
       cfg.dynamicSmemBytes = kClSmemBase + (size_t)h->cluster_cols_words * 4;

@@ -126,4 +126,12 @@ DCS_API int dcs_debug_pcg_stages(dcs_handle* h, int repeats, double* out6) {
   return DCS_OK;
 }
 
+// development probe: per-phase cycle counts of the last k_pcg_cluster solve on this device (see dcs_pcg_cluster.cuh)
+DCS_API int dcs_debug_cluster_cycles(double* out8) {
+  unsigned long long c[8];
+  if (cudaMemcpyFromSymbol(c, dcs::g_cl_cycles, sizeof(c)) != cudaSuccess) return DCS_ERR_CUDA;
+  for (int i = 0; i < 8; ++i) out8[i] = (double)c[i];
+  return DCS_OK;
+}
+
 }  // extern "C"

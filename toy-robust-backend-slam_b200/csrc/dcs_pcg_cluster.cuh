@@ -7,8 +7,8 @@
 // its memory time.  Here ONE cluster of up to eight CTAs (one CTA per 1024-pose chain tile, the sorting window of the
 // row layout) runs every iteration of the solve:
 //   * the tile's preconditioner factors are copied into shared memory ONCE per solve (k_pcg_chain: once per iteration);
-//   * r, w and the own rows of p live in registers for the whole solve (two stored rows per thread); only p goes to
-//     global memory, because it is the operand the other rows gather;
+//   * r and the own rows of p live in registers for the whole solve (two stored rows per thread), w in shared memory;
+//     only p goes to global memory, because it is the operand the other rows gather;
 //   * the three dependencies of an iteration that cross CTAs - p complete before the product, p.q, (r.z, r.r) - are
 //     hardware cluster barriers; the scalar sums travel through distributed shared memory: every CTA stores its partial
 //     into its slot of EVERY CTA's slot array and all CTAs add the slots in rank order, so alpha, beta and the
@@ -30,15 +30,20 @@ constexpr int kClThreads = 512;                        // threads per CTA
 constexpr int kClRows = kChainTile / kClThreads;       // stored rows per thread
 constexpr int kClWarps = kClThreads / 32;
 constexpr int kClMaxTiles = 8;                         // portable cluster size: graphs up to 8192 poses
-// dynamic shared memory: s_v [3][1056] doubles | factors [15][1024] floats | warp partials [3][16] | slots A [1][8], B [2][8]
-// | the CTA's column words (when they fit)
+// dynamic shared memory: s_v [3][1056] doubles (the substitution's vector, chain order) | s_w [3][1024] doubles (storage
+// order) | the tile's factors [15][1024] floats | warp partials [3][16] | slots A [1][8], B [2][8] | the CTA's column
+// words (when they fit).  Kept small on purpose: what shared memory takes, L1 loses, and the product
+// phase needs L1 lines for its loads in flight (profiles/r02_small_graphs.md: with 225 KB of shared memory the same
+// product loop takes 16.8 K instead of 10.2 K cycles).
 constexpr size_t kClSmemVec = 3 * (kChainTile + 32) * sizeof(double);
+constexpr size_t kClSmemRow = 3 * kChainTile * sizeof(double);
 constexpr size_t kClSmemFac = 15 * kChainTile * sizeof(float);
 constexpr size_t kClSmemRed = (3 * kClWarps + 3 * kClMaxTiles) * sizeof(double);
-constexpr size_t kClSmemBase = kClSmemVec + kClSmemFac + kClSmemRed;
-constexpr size_t kClSmemMax = 200 * 1024;              // base + staged column words stay below this
+constexpr size_t kClSmemBase = kClSmemVec + kClSmemRow + kClSmemFac + kClSmemRed;
+constexpr size_t kClSmemMax = 163 * 1024;              // stay inside the 164-KB shared-memory configuration (92 KB of L1 remain)
+constexpr int kClMaxColWords = (int)((kClSmemMax - kClSmemBase) / sizeof(uint32_t));
 static_assert(kClRows * kClThreads == kChainTile && kChainTile == kWindow, "one CTA per 1024-row window");
-static_assert(kClSmemVec % 16 == 0 && (kClSmemVec + kClSmemFac) % 16 == 0 && kClSmemBase % 16 == 0, "shared-memory carve-up alignment");
+static_assert(kClSmemVec % 16 == 0 && kClSmemRow % 16 == 0 && kClSmemFac % 16 == 0 && kClSmemBase % 16 == 0, "shared-memory carve-up alignment");
 
 // p is written by other CTAs of the cluster during the kernel: read it through L2 (never the non-coherent path, never a
 // line L1 kept from the previous iteration)
@@ -153,10 +158,20 @@ __device__ __forceinline__ void chain_substitute(double (*s_v)[kChainTile + 32],
   }
 }
 
+#ifdef DCS_DEV_PROBES
+// development build only: cycles thread 0 of CTA 0 spent in each phase of the iteration loop, summed over the solve
+// (dcs_debug_cluster_cycles): 0 barrier before the product, 1 product, 2 p.q exchange, 3 vector update + staging,
+// 4 substitution, 5 z + (r.z, r.r) exchange, 6 direction, 7 iterations
+__device__ unsigned long long g_cl_cycles[8];
+#define DCS_CL_MARK(i) do { if (t == 0 && me == 0) { const long long c_ = clock64(); cyc[i] += c_ - tlast; tlast = c_; } } while (0)
+#else
+#define DCS_CL_MARK(i) do { } while (0)
+#endif
+
 // Solve (offdiag blocks + D) w = rhs (rhs masked to the parameter rows) by PCG with the chain preconditioner whose
 // factors k_chain_factor left in chL / chS.  grid = cluster = ntiles CTAs (<= kClMaxTiles).  Results: w (storage order
 // SoA), scal[S_RR0] = |rhs|^2, scal[S_RR] = |r|^2 at exit, scal[S_PCG_ITERS] = iterations run (a multiple of `batch`).
-// max_iter must be a multiple of batch.
+// max_iter must be a multiple of batch.  cols_smem_words: column words a CTA may stage (0: read `cols`).
 __global__ void __launch_bounds__(kClThreads, 1)
 k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_free, RowLayout L, const uint32_t* __restrict__ cols,
               const double* __restrict__ Hoff, const double* __restrict__ D, const float* __restrict__ chL,
@@ -165,11 +180,12 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char s_raw[];
   double (*s_v)[kChainTile + 32] = reinterpret_cast<double (*)[kChainTile + 32]>(s_raw);
-  float (*s_L)[kChainTile] = reinterpret_cast<float (*)[kChainTile]>(s_raw + kClSmemVec);     // [9][step * 32 + segment]
-  float (*s_S)[kChainTile] = s_L + 9;                                                         // [6][step * 32 + segment]
-  double* s_warp = reinterpret_cast<double*>(s_raw + kClSmemVec + kClSmemFac);                // [3][kClWarps]
-  double* s_slotA = s_warp + 3 * kClWarps;                                                    // [1][kClMaxTiles]: p.q
-  double* s_slotB = s_slotA + kClMaxTiles;                                                    // [2][kClMaxTiles]: r.z, r.r
+  double (*s_w)[kChainTile] = reinterpret_cast<double (*)[kChainTile]>(s_raw + kClSmemVec);                  // w, storage order
+  float (*s_L)[kChainTile] = reinterpret_cast<float (*)[kChainTile]>(s_raw + kClSmemVec + kClSmemRow);       // [9][step * 32 + segment]
+  float (*s_S)[kChainTile] = s_L + 9;                                                                        // [6][step * 32 + segment]
+  double* s_warp = reinterpret_cast<double*>(s_raw + kClSmemVec + kClSmemRow + kClSmemFac);                  // [3][kClWarps]
+  double* s_slotA = s_warp + 3 * kClWarps;                                                                   // [1][kClMaxTiles]: p.q
+  double* s_slotB = s_slotA + kClMaxTiles;                                                                   // [2][kClMaxTiles]: r.z, r.r
   uint32_t* s_cols = reinterpret_cast<uint32_t*>(s_raw + kClSmemBase);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const unsigned me = cl.block_rank(), nb = cl.num_blocks();
@@ -191,13 +207,13 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
   if (cols_staged)
     for (int64_t i = t; i < n_words; i += kClThreads) s_cols[i] = cols[first_tile * kSlice + i];
 
-  int64_t row[kClRows];
+  int32_t row[kClRows];                                        // stored rows of this thread (< 8192: 32-bit state, fewer registers)
   bool in[kClRows];
   int deg[kClRows], sn[kClRows];
-  int64_t rtile[kClRows];                                      // first SELL tile of the row's task
+  int32_t rtile[kClRows];                                      // first SELL tile of the row's task
 #pragma unroll
   for (int u = 0; u < kClRows; ++u) {
-    row[u] = row0 + u * kClThreads + t;
+    row[u] = (int32_t)row0 + u * kClThreads + t;
     in[u] = row[u] < L.nrows;
     deg[u] = in[u] ? (int)L.rowinfo[row[u]].x : 0;
     rtile[u] = L.task_info[row[u] >> 5].x;
@@ -205,8 +221,8 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
     sn[u] = n + (n >> 5);
   }
 
-  // initialisation: w = 0, r = rhs (masked), z = M^-1 r, p = z
-  double r[kClRows][3], p[kClRows][3], wv[kClRows][3];
+  // initialisation: w = 0, r = rhs (masked), z = M^-1 r, p = z.  An s_w entry is touched by its own thread only.
+  double r[kClRows][3], p[kClRows][3];
   double rr_part = 0.0, rz_part = 0.0;
 #pragma unroll
   for (int u = 0; u < kClRows; ++u) {
@@ -214,7 +230,7 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       r[u][c] = f ? rhs[c * ldn + row[u]] : 0.0;
-      wv[u][c] = 0.0;
+      s_w[c][u * kClThreads + t] = 0.0;
       s_v[c][sn[u]] = r[u][c];
     }
     rr_part = fma(r[u][0], r[u][0], fma(r[u][1], r[u][1], fma(r[u][2], r[u][2], rr_part)));
@@ -238,11 +254,16 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
   int it = 0;
   if (rr0 > 0.0 && isfinite(rr0)) {                            // the same value in every thread of the cluster
     const double target = rel_tol * rel_tol * rr0;
+#ifdef DCS_DEV_PROBES
+    long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     while (it < max_iter) {
       // every row of p (written above / at the end of the previous iteration) before anyone gathers it: the barrier's
       // arrive.release / wait.acquire orders the global stores of all threads of the cluster before the gathers below
       cl.sync();
-      // q = A p over the thread's rows (k_spmv's row walk), p.q
+      DCS_CL_MARK(0);
+      // q = A p over the thread's rows (k_spmv's row walk: diagonal block first, rounds in order), p.q.  Every access of
+      // the phase goes to L2: the barrier invalidated L1, and p comes from the other CTAs.
       double y[kClRows][3];
       double dot = 0.0;
 #pragma unroll
@@ -254,8 +275,8 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
           double y0 = fma(a00, p[u][0], fma(a01, p[u][1], a02 * p[u][2]));
           double y1 = fma(a01, p[u][0], fma(a11, p[u][1], a12 * p[u][2]));
           double y2 = fma(a02, p[u][0], fma(a12, p[u][1], a22 * p[u][2]));
-          const uint32_t* cp = cols_staged ? s_cols + (rtile[u] - first_tile) * kSlice + lane : cols + rtile[u] * kSlice + lane;   // round k: + 32 k
-          const double* hp = Hoff + rtile[u] * (kBlockVals * 32) + lane;                        // round k: + 256 k, value c: + 32 c
+          const uint32_t* cp = cols_staged ? s_cols + (rtile[u] - (int32_t)first_tile) * kSlice + lane : cols + (int64_t)rtile[u] * kSlice + lane;   // round k: + 32 k
+          const double* hp = Hoff + (int64_t)rtile[u] * (kBlockVals * 32) + lane;                        // round k: + 256 k, value c: + 32 c
           constexpr int U = 2;                                 // rounds in flight per row
           int k = 0;
           for (; k + U <= deg[u]; k += U) {
@@ -290,8 +311,10 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
           dot = fma(p[u][0], y0, fma(p[u][1], y1, fma(p[u][2], y2, dot)));
         }
       }
+      DCS_CL_MARK(1);
       double v1[1] = {dot};
       cluster_sum<1>(cl, v1, s_warp, s_slotA, t, me, nb);
+      DCS_CL_MARK(2);
       const double pq = v1[0];
       const double alpha = (pq != 0.0) ? rz / pq : 0.0;
       // w += alpha p, r -= alpha q, r staged in the chain's order
@@ -301,14 +324,16 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           r[u][c] = fma(-alpha, y[u][c], r[u][c]);
-          wv[u][c] = fma(alpha, p[u][c], wv[u][c]);
+          s_w[c][u * kClThreads + t] = fma(alpha, p[u][c], s_w[c][u * kClThreads + t]);
           s_v[c][sn[u]] = r[u][c];
         }
         rr_part = fma(r[u][0], r[u][0], fma(r[u][1], r[u][1], fma(r[u][2], r[u][2], rr_part)));
       }
       __syncthreads();
+      DCS_CL_MARK(3);
       if (wid == 0) chain_substitute(s_v, s_L, s_S, lane);      // z = M^-1 r
       __syncthreads();
+      DCS_CL_MARK(4);
       double z[kClRows][3];
       rz_part = 0.0;
 #pragma unroll
@@ -319,6 +344,7 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
       }
       v2[0] = rz_part; v2[1] = rr_part;
       cluster_sum<2>(cl, v2, s_warp, s_slotB, t, me, nb);
+      DCS_CL_MARK(5);
       const double rz_next = v2[0];
       rr = v2[1];
       const double beta = (rz != 0.0) ? rz_next / rz : 0.0;
@@ -331,12 +357,23 @@ k_pcg_cluster(const double* __restrict__ rhs, const uint8_t* __restrict__ is_fre
         if (in[u]) p4[row[u]] = make_double4(p[u][0], p[u][1], p[u][2], 0.0);
       }
       ++it;
+      DCS_CL_MARK(6);
       if (it % batch == 0 && !(rr > target)) break;            // converged, or NaN (the caller validates the step)
     }
+#ifdef DCS_DEV_PROBES
+    if (t == 0 && me == 0) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) g_cl_cycles[i] = (unsigned long long)cyc[i];
+      g_cl_cycles[7] = (unsigned long long)it;
+    }
+#endif
   }
 #pragma unroll
   for (int u = 0; u < kClRows; ++u)
-    if (in[u]) { w[0 * ldn + row[u]] = wv[u][0]; w[1 * ldn + row[u]] = wv[u][1]; w[2 * ldn + row[u]] = wv[u][2]; }
+    if (in[u]) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) w[c * ldn + row[u]] = s_w[c][u * kClThreads + t];
+    }
   if (me == 0 && t == 0) { scal[S_RR0] = rr0; scal[S_RR] = rr; scal[S_RZ] = rz; scal[S_PCG_ITERS] = (double)it; }
 }
 
