@@ -91,7 +91,8 @@ typedef struct dcs_options {
   /* linear solver: preconditioned CG on the 3x3-block normal equations (see `preconditioner`) */
   double pcg_rel_tol;             /* stop when |r|_2 <= pcg_rel_tol * |rhs|_2            */
   int32_t pcg_max_iter;
-  int32_t pcg_check_every;        /* iterations per graph launch between host checks     */
+  int32_t pcg_check_every;        /* iterations between convergence tests (one CUDA-graph launch; on graphs of <= 8192
+                                   * poses the whole solve is one kernel and the test runs inside it at this period) */
   int32_t preconditioner;         /* 0: 3x3 block-Jacobi; 1 (default): block-Jacobi over chain segments of 32 poses
                                    * (each block = the block-tridiagonal odometry-chain part of the segment,
                                    * factorised exactly once per LM iteration)                                    */
