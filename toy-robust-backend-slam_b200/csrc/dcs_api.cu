@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,19 +60,61 @@ std::atomic<int64_t> g_launches{0};    // dcs_solve_batch drives several handles
     ++g_launches; ++t_launches;                                                                  \
   } while (0)
 
+// dcs_solve_batch creates and destroys a handle per item from several host threads.  cudaFree synchronises the whole
+// device, so with plain cudaMalloc / cudaFree every release in one thread waits for the kernels of all the others (the
+// one-launch PCG of a small graph runs for milliseconds).  While tl_pool_stream is set (dcs_create called from a batch
+// worker, single-rank handles only: CUDA IPC needs cudaMalloc memory) device buffers come from the stream-ordered pool
+// instead: allocated and released in the order of the handle's own stream, no device-wide synchronisation.
+thread_local cudaStream_t tl_pool_stream = nullptr;
+thread_local bool tl_batch_worker = false;
+
+// Page-locked staging buffers of a batch worker's handles: cudaMallocHost / cudaFreeHost cost a driver round trip each and
+// cudaFreeHost synchronises the device like cudaFree, so a worker keeps the blocks of the handle it just destroyed for
+// the handle it creates next (same thread) and returns them when it leaves dcs_solve_batch.
+struct PinnedCache {
+  std::vector<std::pair<void*, size_t>> blocks;
+  void clear() { for (auto& b : blocks) cudaFreeHost(b.first); blocks.clear(); }
+  ~PinnedCache() { clear(); }
+};
+thread_local PinnedCache tl_pinned;
+cudaError_t pinned_get(void** p, size_t bytes, size_t* cap) {
+  if (tl_batch_worker) {
+    size_t best = tl_pinned.blocks.size();      // best fit: the three blocks of a handle differ by orders of magnitude
+    for (size_t i = 0; i < tl_pinned.blocks.size(); ++i)
+      if (tl_pinned.blocks[i].second >= bytes && (best == tl_pinned.blocks.size() || tl_pinned.blocks[i].second < tl_pinned.blocks[best].second)) best = i;
+    if (best < tl_pinned.blocks.size()) {
+      *p = tl_pinned.blocks[best].first; *cap = tl_pinned.blocks[best].second;
+      tl_pinned.blocks.erase(tl_pinned.blocks.begin() + (long)best);
+      return cudaSuccess;
+    }
+  }
+  *cap = bytes;
+  return cudaMallocHost(p, bytes);
+}
+void pinned_put(void* p, size_t cap) {
+  if (!p) return;
+  if (tl_batch_worker && tl_pinned.blocks.size() < 16) tl_pinned.blocks.emplace_back(p, cap);
+  else cudaFreeHost(p);
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t pool_stream = nullptr;      // set when p came from cudaMallocAsync: released on the same stream
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() {
+    if (p) { if (pool_stream) cudaFreeAsync(p, pool_stream); else cudaFree(p); }
+    p = nullptr; n = 0; pool_stream = nullptr;
+  }
   cudaError_t alloc(size_t count) {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
+    if (tl_pool_stream) { pool_stream = tl_pool_stream; return cudaMallocAsync(&p, count * sizeof(T), pool_stream); }
     return cudaMalloc(&p, count * sizeof(T));
   }
   // zero-fill ordered on the handle's (non-blocking) stream: a plain cudaMemset goes to the legacy default stream,
@@ -267,6 +310,7 @@ struct dcs_handle {
   DevBuf<unsigned int> tickets;
   double* h_scal = nullptr;                // pinned mirror of scal
   double* h_pin3 = nullptr;                // pinned N x 3 staging
+  size_t h_scal_cap = 0, h_rank_scal_cap = 0, h_pin3_cap = 0;      // capacities of the three pinned blocks (pinned_put)
   cudaGraphExec_t pcg_graph = nullptr;
   bool cluster_pcg = false;                // small single-rank graph with the chain preconditioner: k_pcg_cluster runs the whole solve
   int32_t cluster_cols_words = 0;          // column words k_pcg_cluster may stage in shared memory (0: read them from global memory)
@@ -875,16 +919,18 @@ void dcs_destroy(dcs_handle* h) {
   if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
   for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
   if (h->comm) nccl_api().CommDestroy(h->comm);
-  if (h->h_scal) cudaFreeHost(h->h_scal);
-  if (h->h_rank_scal) cudaFreeHost(h->h_rank_scal);
-  if (h->h_pin3) cudaFreeHost(h->h_pin3);
+  if (h->stream) cudaStreamSynchronize(h->stream);      // nothing in flight may still write the pinned blocks a batch worker reuses
+  pinned_put(h->h_pin3, h->h_pin3_cap);
+  pinned_put(h->h_scal, h->h_scal_cap);
+  pinned_put(h->h_rank_scal, h->h_rank_scal_cap);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->stream2) cudaStreamDestroy(h->stream2);
-  if (h->stream) cudaStreamDestroy(h->stream);
-  delete h;
+  cudaStream_t s1 = h->stream, s2 = h->stream2;
+  delete h;                 // the device buffers first: pool memory is released in the order of the handle's stream
+  if (s2) cudaStreamDestroy(s2);
+  if (s1) cudaStreamDestroy(s1);
 }
 
 int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
@@ -937,6 +983,8 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   if (h->rank < 0 || h->rank >= h->world) { g_err = "dcs_create: bad rank"; return DCS_ERR_ARG; }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  struct PoolScope { ~PoolScope() { tl_pool_stream = nullptr; } } pool_scope;      // every return below leaves pool mode
+  if (tl_batch_worker && o->world <= 1) tl_pool_stream = h->stream;
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
@@ -1099,16 +1147,26 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
     const bool want = !(ev && std::atoi(ev) == 0);
     if (want && h->world == 1 && h->opt.preconditioner == 1 && h->ntiles >= 1 && h->ntiles <= kClMaxTiles) {
       h->cluster_cols_words = h->ldh <= (int64_t)kClMaxColWords ? (int32_t)h->ldh : 0;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)h->ntiles); cfg.blockDim = dim3(kClThreads);
-      cfg.dynamicSmemBytes = kClSmemBase + (size_t)h->cluster_cols_words * 4;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = (unsigned)h->ntiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      int n_clusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&n_clusters, k_pcg_cluster, &cfg) == cudaSuccess && n_clusters >= 1) h->cluster_pcg = true;
-      else (void)cudaGetLastError();       // a device that cannot co-schedule the cluster: general path
+      // Can the device co-schedule a cluster of this many CTAs?  Asked once per (device, cluster size) with the largest
+      // shared-memory request a launch can make and remembered: the occupancy query costs milliseconds and is serialised
+      // by the driver, and dcs_solve_batch creates a handle per item from several host threads.
+      static std::mutex mu;
+      static signed char known[64][kClMaxTiles + 1];        // 0: not asked yet, 1: yes, -1: no
+      const int dslot = h->dev & 63;
+      std::lock_guard<std::mutex> lock(mu);
+      if (known[dslot][h->ntiles] == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)h->ntiles); cfg.blockDim = dim3(kClThreads);
+        cfg.dynamicSmemBytes = kClSmemMax;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)h->ntiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, k_pcg_cluster, &cfg) == cudaSuccess && n_clusters >= 1) known[dslot][h->ntiles] = 1;
+        else { (void)cudaGetLastError(); known[dslot][h->ntiles] = -1; }      // cannot co-schedule the cluster: general path
+      }
+      h->cluster_pcg = known[dslot][h->ntiles] == 1;
     }
   }
   CK(h->chL.alloc_zero(9 * LN, st)); CK(h->chS.alloc_zero(6 * LN, st));
@@ -1116,10 +1174,10 @@ int dcs_create(const dcs_graph* g, const dcs_options* o, dcs_handle** out) {
   if (h->nrows > 0) LAUNCH(k_chain_entries, cdiv(h->nrows, 256), 256, st, h->keys.p, nh, h->row_lo, h->nrows, h->chain_idx.p, h->chain_cnt.p);
   CK(h->task_part.alloc_zero((size_t)3 * std::max(h->nblk, (int32_t)(h->ldn / kChainTile) + 1), st));
   CK(h->stage3.alloc_zero((size_t)h->Npad * 3, st));
-  CK(cudaMallocHost(&h->h_scal, S_COUNT * sizeof(double)));
+  CK(pinned_get((void**)&h->h_scal, S_COUNT * sizeof(double), &h->h_scal_cap));
   CK(h->rank_scal.alloc_zero((size_t)h->world * 4, st));
-  CK(cudaMallocHost(&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double)));
-  CK(cudaMallocHost(&h->h_pin3, (size_t)N * 3 * sizeof(double)));
+  CK(pinned_get((void**)&h->h_rank_scal, (size_t)h->world * 4 * sizeof(double), &h->h_rank_scal_cap));
+  CK(pinned_get((void**)&h->h_pin3, (size_t)N * 3 * sizeof(double), &h->h_pin3_cap));
   if (h->sc) {
     CK(h->sw.alloc(EE)); CK(h->sw_cand.alloc(EE)); CK(h->sw_scale.alloc(EE));
     CK(h->sw_slot.alloc_zero(HH, st));
@@ -1596,7 +1654,17 @@ int dcs_solve_batch(dcs_batch_item* items, int32_t n_items, const dcs_options* o
   const int nt = std::max(1, std::min<int>({n_threads > 0 ? n_threads : 8, n_items, 64}));
   std::atomic<int32_t> next{0};
   std::vector<std::string> errs((size_t)n_items);
+  {   // keep released pool memory cached between items (default: returned to the driver at every synchronisation)
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaSetDevice(options->device) == cudaSuccess && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
   auto worker = [&]() {
+    struct Mode { Mode() { tl_batch_worker = true; } ~Mode() { tl_batch_worker = false; tl_pinned.clear(); } } mode;
     for (;;) {
       const int32_t i = next.fetch_add(1);
       if (i >= n_items) return;
