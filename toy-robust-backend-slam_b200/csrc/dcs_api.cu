@@ -1654,13 +1654,17 @@ int dcs_solve_batch(dcs_batch_item* items, int32_t n_items, const dcs_options* o
   const int nt = std::max(1, std::min<int>({n_threads > 0 ? n_threads : 8, n_items, 64}));
   std::atomic<int32_t> next{0};
   std::vector<std::string> errs((size_t)n_items);
-  {   // keep released pool memory cached between items (default: returned to the driver at every synchronisation)
+  // keep released pool memory cached between items for the duration of the batch (default: returned to the driver at
+  // every synchronisation); the previous threshold is restored and the pool trimmed when the batch is done
+  cudaMemPool_t pool = nullptr;
+  uint64_t old_threshold = 0;
+  {
     int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaSetDevice(options->device) == cudaSuccess && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    if (cudaSetDevice(options->device) == cudaSuccess && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &old_threshold) == cudaSuccess) {
       uint64_t keep = UINT64_MAX;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+    } else pool = nullptr;
     (void)cudaGetLastError();
   }
   auto worker = [&]() {
@@ -1688,6 +1692,12 @@ int dcs_solve_batch(dcs_batch_item* items, int32_t n_items, const dcs_options* o
     std::vector<std::thread> pool;
     for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
+  }
+  if (pool) {
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &old_threshold);
+    cudaDeviceSynchronize();                 // every stream-ordered release of the batch has happened
+    cudaMemPoolTrimTo(pool, 0);
+    (void)cudaGetLastError();
   }
   for (int32_t i = 0; i < n_items; ++i)
     if (items[i].status != DCS_OK) { g_err = "dcs_solve_batch: item " + std::to_string(i) + ": " + errs[(size_t)i]; return items[i].status; }
